@@ -1,0 +1,219 @@
+"""Mandatory OM analyses: DCE, allocation, valid-region, write grouping.
+
+Mirrors Language/Paraiso/Optimization.hs:28-53 (all levels O0..O3 run the same pipeline:
+deadCodeElimination -> decideAllocation -> boundaryAnalysis -> writeGrouping) and the four
+passes under Language/Paraiso/Optimization/.  The passes annotate nodes in place of the
+reference's functional `imap`; results are checked against the reference's annotated graph
+dumps (examples-old/*-exampled/output/OM.txt) and the manifest/subkernel lists visible in
+examples-old/*-exampled/dist/*.hpp.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Set
+
+from . import annotation as A
+from .om.graph import ARRAY, SCALAR, Graph, Kernel, Node, OM
+
+LEVELS = {"Unoptimized": -1, "O0": 0, "O1": 1, "O2": 2, "O3": 3}
+
+
+# ---------------------------------------------------------------------------------------------
+# DeadCodeElimination.hs:19-70
+# ---------------------------------------------------------------------------------------------
+def dead_code_elimination(g: Graph) -> Graph:
+    n = g.no_nodes()
+    alive = [False] * n
+    # memoAlive: Store and Load are roots; otherwise alive iff any successor is alive.
+    # successors always have larger ids, so one reverse sweep is the fixed point.
+    for i in range(n - 1, -1, -1):
+        nd = g.nodes[i]
+        if nd.inst is not None and nd.inst.op in ("Store", "Load"):
+            alive[i] = True
+        else:
+            alive[i] = any(alive[s] for s in nd.suc)
+    old2new: Dict[int, int] = {}
+    for i in range(n):
+        if alive[i]:
+            old2new[i] = len(old2new)
+    g2 = Graph()
+    for i in range(n):
+        if not alive[i]:
+            continue
+        nd = g.nodes[i]
+        new = Node(value=nd.value, inst=nd.inst, anot=A.set_(A.Alive(True), nd.anot))
+        g2.add([old2new[p] for p in nd.pre if p in old2new], new)
+    return g2
+
+
+# ---------------------------------------------------------------------------------------------
+# DecideAllocation.hs:25-83
+# ---------------------------------------------------------------------------------------------
+def decide_allocation(g: Graph) -> Graph:
+    for i, nd in enumerate(g.nodes):
+        pre0 = g.nodes[nd.pre[0]] if nd.pre else None
+        sucs = [g.nodes[s] for s in nd.suc]
+
+        def pre_is(op):
+            return pre0 is not None and pre0.inst is not None and pre0.inst.op == op
+
+        def suc_is(op):
+            return any(s.inst is not None and s.inst.op == op for s in sucs)
+
+        if pre_is("Load"):
+            nd.anot = A.set_(A.Existing, nd.anot)
+        elif suc_is("Store") or suc_is("Reduce") or pre_is("Reduce") or suc_is("Broadcast") or pre_is("Broadcast"):
+            nd.anot = A.set_(A.Manifest, nd.anot)
+        else:
+            # weakSet Delayed . setChoice  (setChoice is applied first)
+            if nd.is_value:
+                nd.anot = A.set_(A.AllocationChoice((A.Delayed, A.Manifest)), nd.anot)
+            nd.anot = A.weak_set(A.Delayed, nd.anot)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# BoundaryAnalysis.hs:33-103
+# ---------------------------------------------------------------------------------------------
+def boundary_analysis(g: Graph, dim: int) -> Graph:
+    full = A.Valid(tuple(A.Interval(A.lower_boundary(0), A.upper_boundary(0)) for _ in range(dim)))
+    infinite = A.Valid(tuple(A.Interval(A.NEGA_INF, A.POSI_INF) for _ in range(dim)))
+    memo: List[A.Valid] = []
+
+    def add(x, nby):
+        if nby[0] in (0, 3):
+            return nby
+        return (nby[0], nby[1] + x)
+
+    for i, nd in enumerate(g.nodes):
+        if nd.is_value:
+            if nd.value.realm == SCALAR:
+                v = infinite
+            else:
+                assert len(nd.pre) == 1, f"node[{i}] only 1 pre expected"
+                v = memo[nd.pre[0]]
+        else:
+            op = nd.inst.op
+            if op in ("Imm", "Reduce", "Broadcast", "LoadIndex", "LoadSize"):
+                v = infinite
+            elif op == "Load":
+                v = full
+            elif op == "Store":
+                v = memo[nd.pre[0]]
+            elif op == "Shift":
+                pre = memo[nd.pre[0]]
+                shifted = []
+                for x, iv in zip(nd.inst.arg, pre.intervals):
+                    if iv.lower is None:
+                        raise ValueError("empty interval raised!")
+                    shifted.append(A.Interval(add(x, iv.lower), add(x, iv.upper)))
+                v = full.intersection(A.Valid(tuple(shifted)))
+            elif op == "Arith":
+                assert nd.pre, f"arith node[{i}] has 0 pre"
+                v = memo[nd.pre[0]]
+                for p in nd.pre[1:]:
+                    v = v.intersection(memo[p])
+            else:
+                raise ValueError(op)
+        memo.append(v)
+        nd.anot = A.set_(v, nd.anot)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# DependencyAnalysis.hs:67-258
+# ---------------------------------------------------------------------------------------------
+def dependency_analysis(g: Graph) -> Graph:
+    n = g.no_nodes()
+    alloc = []
+    for i, nd in enumerate(g.nodes):
+        a = A.to_maybe(A.Allocation, nd.anot)
+        if a is None:
+            raise ValueError("writeGrouping must be done after decideAllocation")
+        alloc.append(a)
+    strict = [a in (A.Manifest, A.Existing) for a in alloc]
+
+    dep_write: List[frozenset] = [frozenset()] * n
+    ind_write: List[frozenset] = [frozenset()] * n
+    calc_write: List[frozenset] = [frozenset()] * n
+    for i, nd in enumerate(g.nodes):
+        dw: Set[int] = set()
+        iw: Set[int] = set()
+        cw: Set[int] = set()
+        for p in nd.pre:
+            if strict[p]:
+                dw.add(p)
+                iw.add(p)
+                iw |= ind_write[p]
+                cw.add(p)
+            else:
+                dw |= dep_write[p]
+                iw |= ind_write[p]
+                cw.add(p)
+                cw |= calc_write[p]
+        dep_write[i], ind_write[i], calc_write[i] = frozenset(dw), frozenset(iw), frozenset(cw)
+
+    manifest = [i for i in range(n) if alloc[i] == A.Manifest]
+    group: Dict[int, int] = {}
+
+    def realm_of(i):
+        nd = g.nodes[i]
+        if not nd.is_value:
+            raise ValueError("realm required for non-Value node")
+        return nd.value.realm
+
+    def valid_of(i):
+        return A.to_maybe(A.Valid, g.nodes[i].anot)
+
+    def coexist(idx, jdx):  # DependencyAnalysis.hs:125-136 (idx > jdx)
+        if idx == jdx:
+            return True
+        if idx < jdx:
+            idx, jdx = jdx, idx
+        dependent = jdx in ind_write[idx]
+        same = realm_of(idx) == realm_of(jdx) and valid_of(idx) == valid_of(jdx)
+        return (not dependent) and same
+
+    for k, idx in enumerate(manifest):
+        pres = manifest[:k]
+        if not pres:
+            group[idx] = 0
+            continue
+        existing = sorted({group[p] for p in pres})
+        co = [grp for grp in existing if all(coexist(idx, m) for m in pres if group[m] == grp)]
+        group[idx] = co[0] if co else 1 + max(group[p] for p in pres)
+
+    for i, nd in enumerate(g.nodes):
+        an = nd.anot
+        an = A.set_(A.Indirect(tuple(sorted(ind_write[i]))), an)
+        an = A.set_(A.Direct(tuple(sorted(dep_write[i]))), an)
+        an = A.set_(A.Calc(calc_write[i]), an)
+        if alloc[i] == A.Manifest:
+            an = A.set_(A.KernelWriteGroup(group[i]), an)
+        nd.anot = an
+    return g
+
+
+def write_grouping(om: OM) -> OM:  # DependencyAnalysis.hs:37-64
+    diff = 0
+    for k in om.kernels:
+        dependency_analysis(k.dataflow)
+        cnt = 1 + max([-1] + [kw.gid for nd in k.dataflow.nodes for kw in A.to_list(A.KernelWriteGroup, nd.anot)])
+        for nd in k.dataflow.nodes:
+            nd.anot = [A.OMWriteGroup(y.gid + diff) if type(y) is A.KernelWriteGroup else y for y in nd.anot]
+        diff += cnt
+    return om
+
+
+def optimize(level: str, om: OM) -> OM:  # Optimization.hs:28-53
+    lv = LEVELS[level]
+    old = A.to_maybe(A.OptLevel, om.setup.global_annotation)
+    if old is not None and lv <= old.level:
+        return om
+    if (old.level if old else -2) < 0 <= lv:
+        for k in om.kernels:
+            k.dataflow = dead_code_elimination(k.dataflow)
+            decide_allocation(k.dataflow)
+            boundary_analysis(k.dataflow, om.dim)
+        write_grouping(om)
+    om.setup.global_annotation = A.set_(A.OptLevel(lv), om.setup.global_annotation)
+    return om
