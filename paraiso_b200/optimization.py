@@ -122,7 +122,7 @@ def boundary_analysis(g: Graph, dim: int) -> Graph:
 # ---------------------------------------------------------------------------------------------
 # DependencyAnalysis.hs:67-258
 # ---------------------------------------------------------------------------------------------
-def dependency_analysis(g: Graph) -> Graph:
+def dependency_analysis(g: Graph, strict_order: bool = True) -> Graph:
     n = g.no_nodes()
     alloc = []
     for i, nd in enumerate(g.nodes):
@@ -180,6 +180,15 @@ def dependency_analysis(g: Graph) -> Graph:
             continue
         existing = sorted({group[p] for p in pres})
         co = [grp for grp in existing if all(coexist(idx, m) for m in pres if group[m] == grp)]
+        if strict_order:
+            # DEVIATION from DependencyAnalysis.hs:108-124, which takes `head coGroups` without
+            # checking that the node's own Manifest dependencies sit in *earlier* groups.  Master's
+            # Hydro (`broadcast $ cast $ loadSize`, HydroMain.hs:112) then runs the Broadcast
+            # subkernel before the Scalar subkernel that produces its input, so the first call
+            # reads a zero-initialised manifest scalar.  The intended order is enforced here; the
+            # plans of every checked-in sample are unchanged by it (tests/test_plan.py).
+            floor = max([group[d] for d in ind_write[idx] if d in group] + [-1])
+            co = [grp for grp in co if grp > floor]
         group[idx] = co[0] if co else 1 + max(group[p] for p in pres)
 
     for i, nd in enumerate(g.nodes):

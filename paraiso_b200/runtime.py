@@ -1,0 +1,290 @@
+"""Host side of a generated machine: the Python mirror of the emitted C++ class.
+
+The reference's emitted class owns every array as a value member and exposes
+`<kernel>()`, `om_size[_k]()`, `om_memory_size[_k]()`, `om_lower/upper_margin_k()`, `name()` and
+`name(i0, i1)` (PlanTrans.hs:50-215).  `Machine` keeps that surface (same names, same argument
+meaning) over the C ABI of lib<Name>.so:
+
+  * arrays live on the device in a padded, pitched layout with ghost zones; a
+    `store` is a pointer swap between two buffers instead of the reference's whole-array copy
+    (PlanTrans.hs:243-258);
+  * scalars live in device slots; host reads synchronise, like the reference's thrust_vector
+    mirror (Generator/draft.cpp:53-132);
+  * with world_size > 1 the grid is slab-decomposed along the outermost axis; ghost rows travel
+    with torch.distributed send/recv (NCCL over NVLink on GPUs), reduce results with all_reduce.
+
+PyTorch supplies device memory, streams and the process group only; every cell update runs in
+the generated CUDA kernels.  There is no CPU fallback: `device` must be a CUDA device unless a
+test passes `_emulated=True` together with a library built by tests/emu.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .annotation import CYCLIC, OPEN
+
+TORCH_TYPE = {"Int": torch.int32, "Float": torch.float32, "Double": torch.float64, "Bool": torch.bool,
+              "Integer": torch.int64}
+NP_TYPE = {"Int": np.int32, "Float": np.float32, "Double": np.float64, "Bool": np.bool_, "Integer": np.int64}
+SM_COUNT = 148
+
+
+class OmGeom(ctypes.Structure):
+    """Mirror of `struct OmGeom` in csrc/om_runtime.cuh."""
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "nx", "ny", "pitch", "rows", "xorg", "yorg", "y0", "nyl",
+        "gx_lo", "gx_hi", "gy_lo", "gy_hi", "cyc_x", "cyc_y", "wrap_y_local",
+        "own_r0", "own_r1", "chunk_rows")]
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def slab_rows(ny: int, nranks: int, rank: int):
+    """Rows [y0, y0+nyl) of the global axis 1 owned by `rank` (remainder rows go to the first ranks)."""
+    base, rem = divmod(ny, nranks)
+    nyl = base + (1 if rank < rem else 0)
+    y0 = rank * base + min(rank, rem)
+    return y0, nyl
+
+
+class Machine:
+    def __init__(self, desc: dict, lib_path: str, size=None, device="cuda", rank: int = 0, nranks: int = 1,
+                 group=None, _emulated: bool = False):
+        self.desc = desc
+        self.name = desc["name"]
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _emulated:
+            raise RuntimeError("paraiso_b200 machines run on CUDA devices only (no CPU fallback)")
+        self.emulated = _emulated
+        self.lib = ctypes.CDLL(lib_path)   # raises OSError if the extension is missing
+        if getattr(self.lib, f"om_{self.name}_abi_version")() != 1:
+            raise RuntimeError("ABI version mismatch")
+        self.rank, self.nranks, self.group = rank, nranks, group
+        size = list(size) if size is not None else list(desc["local_size"])
+        size = size + [1] * (2 - len(size))
+        self.nx, self.ny = int(size[0]), int(size[1])
+        self.boundary = desc["boundary"]
+        self.mlo, self.mhi = desc["lower_margin"], desc["upper_margin"]
+        rlo, rhi = desc["radius_lo"], desc["radius_hi"]
+        self.cyc = [b == CYCLIC for b in self.boundary]
+        for ax in range(2):
+            if not self.cyc[ax]:
+                assert self.mlo[ax] == rlo[ax] and self.mhi[ax] == rhi[ax], "Open margins must equal the stencil radius"
+        self.y0, self.nyl = slab_rows(self.ny, nranks, rank)
+        if nranks > 1 and self.nyl < max(rlo[1], rhi[1]):
+            raise ValueError("slab thinner than the stencil radius")
+        self.gx_lo, self.gx_hi, self.gy_lo, self.gy_hi = rlo[0], rhi[0], rlo[1], rhi[1]
+        self.xorg = _ru(max(self.gx_lo, 1), 32)
+        self.pitch = _ru(self.xorg + self.nx + self.gx_hi, 32)
+        self.yorg = self.gy_lo
+        self.rows = self.nyl + self.gy_lo + self.gy_hi
+        first, last = rank == 0, rank == nranks - 1
+        if self.cyc[1]:
+            self.own_r0, self.own_r1 = self.yorg, self.yorg + self.nyl
+        else:
+            self.own_r0 = 0 if first else self.yorg
+            self.own_r1 = self.rows if last else self.yorg + self.nyl
+        self.cx0, self.cx1 = self.xorg - self.mlo[0], self.xorg + self.nx + self.mhi[0]
+        # storage
+        self.statics = desc["statics"]
+        self.index = {s["name"]: i for i, s in enumerate(self.statics)}
+        self.cur: List[Optional[torch.Tensor]] = []
+        self.alt: List[Optional[torch.Tensor]] = []
+        for s in self.statics:
+            if s["realm"] == "Array":
+                t = TORCH_TYPE[s["type"]]
+                self.cur.append(torch.zeros((self.rows, self.pitch), dtype=t, device=self.device))
+                self.alt.append(torch.zeros((self.rows, self.pitch), dtype=t, device=self.device))
+            else:
+                self.cur.append(None)
+                self.alt.append(None)
+        self.nslots = desc["nslots"]
+        self.sc = torch.zeros(self.nslots, dtype=torch.int64, device=self.device)
+        self.max_blocks = 1 << 16
+        nred = max([len(st["reduces"]) for k in desc["kernels"] for st in k["stages"]] + [1])
+        self.scratch = torch.zeros(256 + 8 * self.max_blocks * nred, dtype=torch.uint8, device=self.device)
+        self.kernels = {k["name"]: k for k in desc["kernels"]}
+        self._ptr_cur = (ctypes.c_void_p * len(self.statics))()
+        self._ptr_alt = (ctypes.c_void_p * len(self.statics))()
+        self._refresh_ptrs()
+        self._fn = {}
+        for k in desc["kernels"]:
+            for st in k["stages"]:
+                f = getattr(self.lib, st["symbol"])
+                f.argtypes = [ctypes.POINTER(OmGeom), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p]
+                f.restype = ctypes.c_int
+                self._fn[st["symbol"]] = f
+            if k["scalars"]:
+                f = getattr(self.lib, k["scalars"])
+                f.argtypes = [ctypes.POINTER(OmGeom), ctypes.c_void_p, ctypes.c_void_p]
+                f.restype = ctypes.c_int
+                self._fn[k["scalars"]] = f
+        self.launches = 0
+        self._geom_cache: Dict[str, OmGeom] = {}
+
+    # ---- reference size accessors (PlanTrans.hs:160-215) ------------------------------------
+    def om_size(self, k=None):
+        return self.nx * self.ny if k is None else (self.nx, self.ny)[k]
+
+    def om_memory_size(self, k=None):
+        m = (self.nx + self.mlo[0] + self.mhi[0], self.ny + self.mlo[1] + self.mhi[1])
+        return m[0] * m[1] if k is None else m[k]
+
+    def om_lower_margin(self, k): return self.mlo[k]
+    def om_upper_margin(self, k): return self.mhi[k]
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _refresh_ptrs(self):
+        for i, s in enumerate(self.statics):
+            self._ptr_cur[i] = self.cur[i].data_ptr() if self.cur[i] is not None else None
+            self._ptr_alt[i] = self.alt[i].data_ptr() if self.alt[i] is not None else None
+
+    def _stream(self):
+        if self.device.type == "cuda":
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def _geom(self, st: dict) -> OmGeom:
+        g = self._geom_cache.get(st["symbol"])
+        if g is not None:
+            return g
+        nrows = self.own_r1 - self.own_r0
+        strips = max(1, -(-(self.cx1 - (self.cx0 // st["V"]) * st["V"]) // st["w_out"]))
+        per_sm = max(1, min(16, (220 * 1024) // max(st["smem"], 1), 2048 // st["NT"]))
+        want = SM_COUNT * per_sm * 2
+        chunks = max(1, min(want // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
+        chunks = max(1, chunks)
+        chunk_rows = -(-nrows // chunks)
+        g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
+                   y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
+                   cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),
+                   wrap_y_local=int(self.cyc[1] and self.nranks == 1),
+                   own_r0=self.own_r0, own_r1=self.own_r1, chunk_rows=chunk_rows)
+        if strips * (-(-nrows // chunk_rows)) > self.max_blocks:
+            raise ValueError("grid too large for the reduction scratch")
+        self._geom_cache[st["symbol"]] = g
+        return g
+
+    # ---- kernels ------------------------------------------------------------------------------
+    def call(self, kernel: str):
+        """Run one OM kernel (`init`, `proceed`, ...) — the emitted member function of that name."""
+        k = self.kernels[kernel]
+        stream = self._stream()
+        for st in k["stages"]:
+            g = self._geom(st)
+            rc = self._fn[st["symbol"]](ctypes.byref(g), self._ptr_cur, self._ptr_alt, self.sc.data_ptr(),
+                                        self.scratch.data_ptr(), stream)
+            if rc != 0:
+                raise RuntimeError(f"{st['symbol']} failed with CUDA error {rc}")
+            self.launches += 1
+            if self.nranks > 1:
+                for r in st["reduces"]:
+                    self._allreduce_slot(r)
+        if k["scalars"]:
+            st0 = k["stages"][0] if k["stages"] else None
+            g = self._geom(st0) if st0 else self._geom(dict(symbol="_sc", V=1, w_out=1, smem=0, NT=32, warmup=0))
+            rc = self._fn[k["scalars"]](ctypes.byref(g), self.sc.data_ptr(), stream)
+            if rc != 0:
+                raise RuntimeError(f"{k['scalars']} failed with CUDA error {rc}")
+            self.launches += 1
+        for s in k["array_stores"]:
+            self.cur[s], self.alt[s] = self.alt[s], self.cur[s]
+        self._refresh_ptrs()
+        if self.nranks > 1:
+            for s in k["array_stores"]:
+                self._exchange_rows(self.cur[s])
+
+    def __getattr__(self, item):
+        ks = self.__dict__.get("kernels", {})
+        if item in ks:
+            return lambda: self.call(item)
+        raise AttributeError(item)
+
+    # ---- multi-rank pieces ------------------------------------------------------------------------
+    def _allreduce_slot(self, r: dict):
+        import torch.distributed as dist
+        op = {"Sum": dist.ReduceOp.SUM, "Min": dist.ReduceOp.MIN, "Max": dist.ReduceOp.MAX}[r["op"]]
+        view = self.sc[r["slot"]:r["slot"] + 1].view(TORCH_TYPE[r["type"]])[:1]
+        dist.all_reduce(view, op=op, group=self.group)
+        if view.element_size() < 8:   # keep the unused half of the slot zero
+            pass
+
+    def _exchange_rows(self, a: torch.Tensor):
+        """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too)."""
+        import torch.distributed as dist
+        n, r = self.nranks, self.rank
+        up, down = (r + 1) % n, (r - 1) % n
+        has_up = self.cyc[1] or r < n - 1
+        has_down = self.cyc[1] or r > 0
+        ops = []
+        y0, y1 = self.yorg, self.yorg + self.nyl
+        if self.gy_lo and has_up:     # my top interior rows are the upper neighbour's lower ghost rows
+            ops.append(dist.P2POp(dist.isend, a[y1 - self.gy_lo:y1], up, group=self.group))
+        if self.gy_hi and has_down:   # my bottom interior rows are the lower neighbour's upper ghost rows
+            ops.append(dist.P2POp(dist.isend, a[y0:y0 + self.gy_hi], down, group=self.group))
+        if self.gy_lo and has_down:
+            ops.append(dist.P2POp(dist.irecv, a[0:self.gy_lo], down, group=self.group))
+        if self.gy_hi and has_up:
+            ops.append(dist.P2POp(dist.irecv, a[y1:y1 + self.gy_hi], up, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _fill_ghosts(self, a: torch.Tensor):
+        """Host-initiated ghost refresh after the host wrote an array (not on the step path)."""
+        x0, x1 = self.xorg, self.xorg + self.nx
+        if self.cyc[0]:
+            if self.gx_lo:
+                a[:, x0 - self.gx_lo:x0] = a[:, x1 - self.gx_lo:x1]
+            if self.gx_hi:
+                a[:, x1:x1 + self.gx_hi] = a[:, x0:x0 + self.gx_hi]
+        if self.nranks > 1:
+            self._exchange_rows(a)
+        elif self.cyc[1]:
+            y0, y1 = self.yorg, self.yorg + self.nyl
+            if self.gy_lo:
+                a[0:self.gy_lo] = a[y1 - self.gy_lo:y1]
+            if self.gy_hi:
+                a[y1:y1 + self.gy_hi] = a[y0:y0 + self.gy_hi]
+
+    # ---- host accessors (PlanTrans.hs:117-157) ------------------------------------------------------
+    def _box(self, with_margin: bool):
+        if with_margin:
+            return slice(self.own_r0, self.own_r1), slice(self.cx0, self.cx1)
+        return slice(self.yorg, self.yorg + self.nyl), slice(self.xorg, self.xorg + self.nx)
+
+    def get(self, name: str, with_margin: bool = False) -> np.ndarray:
+        """Local slab of a static Array as [i1, i0] (axis 0 fastest), optionally with the margins
+        of the reference's memory box that this rank owns; synchronises with the device."""
+        i = self.index[name]
+        ry, rx = self._box(with_margin)
+        return self.cur[i][ry, rx].contiguous().cpu().numpy()
+
+    def set(self, name: str, values: np.ndarray, with_margin: bool = False):
+        i = self.index[name]
+        ry, rx = self._box(with_margin)
+        t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.cur[i].dtype)
+        self.cur[i][ry, rx] = t.to(self.device)
+        self._fill_ghosts(self.cur[i])
+
+    def scalar(self, name: str):
+        s = self.statics[self.index[name]]
+        v = self.sc[self.index[name]:self.index[name] + 1].cpu().numpy()
+        return v.view(NP_TYPE[s["type"]])[0]
+
+    def set_scalar(self, name: str, value):
+        s = self.statics[self.index[name]]
+        z = np.zeros(1, dtype=np.int64)
+        z.view(NP_TYPE[s["type"]])[0] = value
+        self.sc[self.index[name]] = int(z[0])
+
+    def synchronize(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
