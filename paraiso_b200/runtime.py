@@ -201,6 +201,16 @@ class Machine:
             for s in k["array_stores"]:
                 self._exchange_rows(self.cur[s])
 
+    def call_stage(self, kernel: str, idx: int):
+        """Launch a single array stage without the pointer swap (benchmark / profiling hook)."""
+        st = self.kernels[kernel]["stages"][idx]
+        g = self._geom(st)
+        rc = self._fn[st["symbol"]](ctypes.byref(g), self._ptr_cur, self._ptr_alt, self.sc.data_ptr(),
+                                    self.scratch.data_ptr(), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"{st['symbol']} failed with CUDA error {rc}")
+        self.launches += 1
+
     def __getattr__(self, item):
         ks = self.__dict__.get("kernels", {})
         if item in ks:
@@ -272,6 +282,13 @@ class Machine:
         ry, rx = self._box(with_margin)
         t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.cur[i].dtype)
         self.cur[i][ry, rx] = t.to(self.device)
+        self._fill_ghosts(self.cur[i])
+
+    def set_from_host(self, name: str, host: torch.Tensor):
+        """Asynchronous upload of the local interior from a (pinned) host tensor."""
+        i = self.index[name]
+        ry, rx = self._box(False)
+        self.cur[i][ry, rx].copy_(host, non_blocking=True)
         self._fill_ghosts(self.cur[i])
 
     def scalar(self, name: str):

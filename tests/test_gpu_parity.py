@@ -1,0 +1,115 @@
+"""GPU parity tests: the generated sm_100a kernels, driven through the C ABI, against the CPU oracle
+(oracle/plantrans.py, pinned to the reference's generated C++ by tests/test_oracle_pin.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _life_pair(size):
+    from oracle.cpu import OracleMachine
+    from paraiso_b200.examples.life import life_om, life_setup
+    from paraiso_b200.machines import life_machine, life_seed
+    m = life_machine(size)
+    o = OracleMachine(life_setup("master", size=size), life_om("master"), openmp=True, opt="-O3")
+    init = life_seed(size[0], 0, size[1])
+    m.call("init"); o.call("init")
+    m.set("cell", init); o.interior("cell")[...] = init
+    return m, o
+
+
+@pytest.mark.parametrize("size,steps", [((80, 48), 40), ((2048, 2048), 100), ((1000, 777), 25), ((5, 3), 6), ((16384, 16384), 10)])
+def test_life_bit_exact(size, steps):
+    m, o = _life_pair(size)
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+        if t in (0, 9, steps - 1):
+            assert np.array_equal(m.get("cell"), o.interior("cell")), f"cells differ at step {t}"
+            assert int(m.scalar("population")) == int(o.scalar("population")[0])
+    assert int(m.scalar("generation")) == steps == int(o.scalar("generation")[0])
+
+
+def test_life_init_pattern_gosper():
+    """examples/Life/main.cpp:21-28 seeds init-pat.txt through the element accessor on the 80x48 default grid."""
+    from paraiso_b200.machines import life_machine
+    pat = [(0, 4), (0, 5), (1, 4), (1, 5), (10, 4), (10, 5), (10, 6), (11, 3), (11, 7), (12, 2), (12, 8), (13, 2), (13, 8),
+           (14, 5), (15, 3), (15, 7), (16, 4), (16, 5), (16, 6), (17, 5), (20, 2), (20, 3), (20, 4), (21, 2), (21, 3), (21, 4),
+           (22, 1), (22, 5), (24, 0), (24, 1), (24, 5), (24, 6), (34, 2), (34, 3), (35, 2), (35, 3)]
+    m = life_machine((80, 48))
+    m.call("init")
+    c = np.zeros((48, 80), np.int32)
+    for x, y in pat:
+        c[y, x] = 1
+    m.set("cell", c)
+    ref = c.copy()
+    for _ in range(60):   # independent 5-line periodic Life
+        n = sum(np.roll(np.roll(ref, dy, 0), dx, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0))
+        ref = (((ref == 0) & (n == 3)) | ((ref == 1) & (n >= 2) & (n <= 3))).astype(np.int32)
+        m.call("proceed")
+    assert np.array_equal(m.get("cell"), ref)
+    assert int(m.scalar("population")) == int(ref.sum())
+
+
+def _hydro_pair(size, fmad=False):
+    from oracle.cpu import OracleMachine
+    from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+    from paraiso_b200.machines import hydro_machine, hydro_set_params
+    m = hydro_machine(size, fmad=fmad)
+    o = OracleMachine(hydro_setup(size), hydro_om("master"), openmp=True, opt="-O2")
+    hydro_set_params(m, size)
+    for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+        o.scalar(k)[0] = v
+    m.call("init"); o.call("init")
+    return m, o
+
+
+NAMES = ["density", "velocity0", "velocity1", "pressure"]
+
+
+def _conserved(get):
+    rho, v0, v1, p = (get(n).astype(np.float64) for n in NAMES)
+    e = 0.5 * rho * (v0 * v0 + v1 * v1) + p / (5.0 / 3.0 - 1.0)
+    return [rho, rho * v0, rho * v1, e]
+
+
+@pytest.mark.parametrize("size,steps", [((64, 48), 5), ((512, 512), 20), ((1024, 1024), 20), ((700, 333), 8)])
+def test_hydro_exact_build_is_bit_identical(size, steps):
+    """-fmad=false build: every cell of every state array equals the oracle's bit for bit."""
+    m, o = _hydro_pair(size)
+    for n in NAMES:   # CUDA sin vs libm sin differ in the last ulp: compare init loosely, then share ICs
+        a, b = m.get(n, with_margin=True), o.array(n)
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) < 1e-14
+        m.set(n, b, with_margin=True)
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    for n in NAMES:
+        a, b = m.get(n, with_margin=True), o.array(n)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), n
+    assert m.scalar("time") == o.scalar("time")[0]
+
+
+def test_hydro_fma_build_within_tolerance():
+    """FMA-contracted build: conserved variables within 1e-12 relative (north-star tolerance, double)."""
+    size, steps = (512, 512), 20
+    m, o = _hydro_pair(size, fmad=True)
+    for n in NAMES:
+        m.set(n, o.array(n), with_margin=True)
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    ca = _conserved(lambda n: m.get(n))
+    cb = _conserved(lambda n: o.interior(n))
+    for a, b in zip(ca, cb):
+        scale = np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) / scale < 1e-12
+    assert abs(m.scalar("time") - o.scalar("time")[0]) / o.scalar("time")[0] < 1e-12
+
+
+def test_hydro_4096_three_steps():
+    size, steps = (4096, 4096), 3
+    m, o = _hydro_pair(size)
+    for n in NAMES:
+        m.set(n, o.array(n), with_margin=True)
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    for n in NAMES:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
