@@ -31,7 +31,9 @@ from ..native import Setup
 from ..plan import Plan
 from .schedule import KernelSchedule, Op, Stage, schedule_kernel
 
-PF = 2  # cp.async prefetch distance in rows
+import os as _os
+
+PF = int(_os.environ.get("OM_PF", "2"))  # cp.async prefetch distance in rows
 
 
 def c_imm(content, ctype: str) -> str:
@@ -101,7 +103,20 @@ def arith_expr(op: Op, a: List[str]) -> str:
     raise NotImplementedError(o)
 
 
+APRON_ROWS = 16   # allocated (zero-initialised) rows the host must provide above and below every array
+VEC_TYPE = {("int", 4): "int4", ("float", 4): "float4", ("double", 2): "double2", ("int", 2): "int2", ("float", 2): "float2"}
+
+
+def _m(x: int) -> str:
+    return str(x).replace("-", "m")
+
+
 class StageEmitter:
+    """Emits one fused stage.  Everything that does not depend on the row (column predicates, ghost
+    edge tests, thread-uniform arithmetic) is hoisted out of the row loop, and ring slots are kept as
+    loop-carried element offsets (one per (depth, row offset) pair) instead of being recomputed with
+    a modulo per access."""
+
     def __init__(self, om: OM, plan: Plan, ks: KernelSchedule, st: Stage, stage_idx: int, V: int, NT: int):
         self.om, self.plan, self.ks, self.st, self.idx = om, plan, ks, st, stage_idx
         self.ops = ks.ops
@@ -112,20 +127,22 @@ class StageEmitter:
         assert self.W_OUT > 0
         self.RW = NT * V + self.PL + self.PR
         self.name = f"om_{om.name}_{ks.name}_stage{stage_idx}"
-        self.lines: List[str] = []
         self.ring_inputs = [i for i in st.inputs.values() if i.via_smem]
-        self.direct_inputs = [i for i in st.inputs.values() if not i.via_smem]
-        # ring depths: inputs get PF + 1 extra rows for the in-flight async copies
         self.depth: Dict[int, int] = {}
-        for i in self.ring_inputs:
+        for i in self.ring_inputs:        # PF + 1 extra rows for the in-flight async copies
             self.depth[i.vid] = i.depth + PF + 1
         for m in st.mats.values():
             self.depth[m.vid] = m.depth
-        self.lag: Dict[int, int] = {i.vid: i.lag for i in st.inputs.values()}
-        self.lag.update({m.vid: m.lag for m in st.mats.values()})
         self.static_of = {i.vid: i.static_idx for i in st.inputs.values()}
-        self.margin_lo = plan.lower_margin + (0,) * (2 - len(plan.lower_margin))
-        self.margin_hi = plan.upper_margin + (0,) * (2 - len(plan.upper_margin))
+        self.margin_lo = tuple(plan.lower_margin) + (0,) * (2 - len(plan.lower_margin))
+        self.margin_hi = tuple(plan.upper_margin) + (0,) * (2 - len(plan.upper_margin))
+        self.slotvars: Dict[Tuple[int, int], str] = {}     # (depth, row offset c) -> element-offset variable
+        self.uniform_used: Dict[int, None] = {}
+        self.pre: List[str] = []                            # hoisted, before the row loop
+        self.uniform = self._uniform_nodes()
+        # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
+        reach = st.warmup + PF + max([abs(i.lag) + i.depth for i in st.inputs.values()] + [0]) + 1
+        assert reach <= APRON_ROWS, f"stage needs {reach} apron rows"
 
     # ------------------------------------------------------------------------------------------
     def T(self, v) -> str:
@@ -137,14 +154,33 @@ class StageEmitter:
             tot = _ru(tot, 16) + d * self.RW * TYPE_BYTES[self.ops[v].ctype]
         return _ru(tot, 16)
 
-    def emit(self, s=""):
-        self.lines.append(s)
+    def _uniform_nodes(self):
+        """Array-realm values that are the same for every cell (built from Broadcast / Imm only)."""
+        uni = set()
+        for v in sorted(self.ops):
+            op = self.ops[v]
+            if op.realm != ARRAY:
+                continue
+            if op.kind in ("Imm", "Broadcast"):
+                uni.add(v)
+            elif op.kind == "Arith" and all((a in uni) or self.ops[a].realm == SCALAR for a in op.args):
+                uni.add(v)
+            elif op.kind == "Shift" and op.args[0] in uni:
+                uni.add(v)
+        return uni
+
+    def slot_off(self, depth: int, c: int) -> str:
+        if depth == 1:
+            return "0"
+        key = (depth, c % depth)
+        if key not in self.slotvars:
+            self.slotvars[key] = f"so{depth}_{key[1]}"
+        return self.slotvars[key]
 
     # ---- scalar (uniform) values ------------------------------------------------------------
     def scalar_code(self, roots: List[int]) -> List[str]:
         """Evaluate Scalar-realm values from the device scalar table, in id order."""
         ops = self.ops
-        need: List[int] = []
         seen = set()
         stack = list(roots)
         while stack:
@@ -153,9 +189,9 @@ class StageEmitter:
                 continue
             seen.add(v)
             op = ops[v]
-            if op.kind in ("Reduce",):
+            if op.kind == "Reduce":
                 continue
-            stack.extend(a for a in op.args)
+            stack.extend(op.args)
         out = []
         for v in sorted(seen):
             op = ops[v]
@@ -169,54 +205,105 @@ class StageEmitter:
             elif op.kind == "LoadSize":
                 out.append(f"const {T} s{v} = ({T}){'g.nx' if op.inst.arg == 0 else 'g.ny'};")
             elif op.kind == "Arith":
-                out.append(f"const {T} s{v} = {arith_expr(op, ['s%d' % a for a in op.args])};")
+                out.append(f"const {T} s{v} = {self.arith(op, ['s%d' % a for a in op.args])};")
             else:
                 raise NotImplementedError(f"scalar {op.kind}")
         return out
 
+    def arith(self, op: Op, args: List[str]) -> str:
+        """arith_expr plus one exact strength reduction: x / 2^k  ==  x * 2^-k in IEEE arithmetic."""
+        if op.inst.arg == "Div" and op.ctype in ("Float", "Double"):
+            d = self.ops[op.args[1]]
+            if d.kind == "Imm":
+                val = float(imm_value(d.inst.arg, d.ctype))
+                if val != 0.0 and np.isfinite(val):
+                    mant, _e = np.frexp(abs(val))
+                    if mant == 0.5 and np.isfinite(1.0 / val) and abs(1.0 / val) > 1e-300:
+                        return f"({args[0]} * {c_imm(1.0 / val, op.ctype)})"
+        return arith_expr(op, args)
+
+    def uniform_code(self) -> List[str]:
+        ops = self.ops
+        need = set()
+        stack = list(self.uniform_used)
+        while stack:
+            v = stack.pop()
+            if v in need:
+                continue
+            need.add(v)
+            stack.extend(a for a in ops[v].args if ops[a].realm == ARRAY)
+        out = []
+        for v in sorted(need):
+            op = ops[v]
+            T = CPP_TYPE[op.ctype]
+            nm = lambda a: f"s{a}" if ops[a].realm == SCALAR else f"u{a}"
+            if op.kind == "Imm":
+                out.append(f"const {T} u{v} = {c_imm(op.inst.arg, op.ctype)};")
+            elif op.kind == "Broadcast":
+                out.append(f"const {T} u{v} = s{op.args[0]};")
+            elif op.kind == "Shift":
+                out.append(f"const {T} u{v} = u{op.args[0]};")
+            else:
+                out.append(f"const {T} u{v} = {self.arith(op, [nm(a) for a in op.args])};")
+        return out
+
+    def staged_read(self, lines, ring_rd, lag, b, cur, k) -> str:
+        """Read staged value `b` (input or MAT) at cursor `cur` for lane k: shared-memory ring."""
+        V = self.V
+        o = k + cur[0]
+        key = (b, cur[1], o)
+        if key in ring_rd:
+            return ring_rd[key]
+        T = self.T(b)
+        so = self.slot_off(self.depth[b], lag + cur[1])
+        vt = VEC_TYPE.get((T, V))
+        if 0 <= o < V and vt:
+            vn = f"rv{b}_{_m(cur[1])}"
+            lines.append(f"const {vt} {vn} = *reinterpret_cast<const {vt}*>(&ring{b}[{so} + tb]);")
+            for kk in range(V):
+                n2 = f"r{b}_{_m(cur[1])}_{kk}"
+                lines.append(f"const {T} {n2} = {vn}.{'xyzw'[kk]};")
+                ring_rd[(b, cur[1], kk)] = n2
+            return ring_rd[key]
+        nm = f"r{b}_{_m(cur[1])}_{_m(o)}"
+        lines.append(f"const {T} {nm} = ring{b}[{so} + tb + ({o})];")
+        ring_rd[key] = nm
+        return nm
+
     # ---- array values inside one scope ------------------------------------------------------
-    def scope(self, targets: List[int], row: str, is_out: bool) -> Tuple[List[str], Dict]:
-        """SSA statements computing `targets` at cursor 0 for the V lanes of this thread at device
-        row `row`.  Returns (lines, {(vid, lane): expr})."""
+    def scope(self, targets: List[int], lag: int) -> Tuple[List[str], Dict]:
+        """SSA statements computing `targets` at cursor 0 for the V lanes of this thread at device row
+        `row` (= j + lag).  Returns (lines, {(vid, lane): expr})."""
         ops, V = self.ops, self.V
         mats = self.st.mats
         lines: List[str] = []
-        memo: Dict[Tuple[int, Tuple[int, int], int], str] = {}
+        memo: Dict[tuple, str] = {}
         ring_rd: Dict[Tuple[int, int, int], str] = {}
-        slot_rd: Dict[Tuple[int, int], str] = {}
-        local_mats: Dict[int, None] = {}   # MAT targets computed in this scope (usable at cursor 0)
         target_set = set(targets)
 
-        def slot(b, cy):
-            key = (b, cy)
-            if key not in slot_rd:
-                nm = f"sl{b}_{str(cy).replace('-', 'm')}"
-                lines.append(f"const int {nm} = ({row} + {cy} + {1 << 20} * {self.depth[b]}) % {self.depth[b]};")
-                slot_rd[key] = nm
-            return slot_rd[key]
-
         def ring_read(b, cur, k):
-            o = k + cur[0]
-            key = (b, cur[1], o)
-            if key in ring_rd:
-                return ring_rd[key]
-            T = self.T(b)
-            sl = slot(b, cur[1])
-            nm = f"r{b}_{str(cur[1]).replace('-', 'm')}_{str(o).replace('-', 'm')}"
-            bytes_ = TYPE_BYTES[ops[b].ctype]
-            vt = {("int", 4): "int4", ("float", 4): "float4", ("double", 2): "double2",
-                  ("int", 2): "int2", ("float", 2): "float2"}.get((T, V))
-            if 0 <= o < V and vt:
-                vn = f"rv{b}_{str(cur[1]).replace('-', 'm')}"
-                lines.append(f"const {vt} {vn} = *reinterpret_cast<const {vt}*>(&ring{b}[{sl} * RW + PL + tid * V]);")
-                for kk in range(V):
-                    n2 = f"r{b}_{str(cur[1]).replace('-', 'm')}_{kk}"
-                    lines.append(f"const {T} {n2} = {vn}.{'xyzw'[kk]};")
-                    ring_rd[(b, cur[1], kk)] = n2
-                return ring_rd[key]
-            lines.append(f"const {T} {nm} = ring{b}[{sl} * RW + PL + tid * V + ({o})];")
-            ring_rd[key] = nm
-            return nm
+            return self.staged_read(lines, ring_rd, lag, b, cur, k)
+
+        def direct_read(v, cur, k):
+            assert cur[0] == 0, "direct global reads are only scheduled for column offset 0"
+            key = ("direct", v, cur[1])
+            if key not in memo:
+                memo[key] = "1"
+                T = self.T(v)
+                sidx = self.static_of[v]
+                cy = cur[1]
+                tag = f"{v}_{_m(cy)}"
+                vt = VEC_TYPE.get((T, V))
+                # no bounds predicates: the ABI requires OM_APRON_ROWS allocated rows around every array
+                lines.append(f"const {T}* __restrict__ pd{tag} = in{sidx} + (ptrdiff_t)(row + ({cy})) * g.pitch + tc;")
+                if vt:
+                    lines.append(f"const {vt} qd{tag} = __ldg(reinterpret_cast<const {vt}*>(pd{tag}));")
+                    for kk in range(V):
+                        lines.append(f"const {T} d{tag}_{kk} = qd{tag}.{'xyzw'[kk]};")
+                else:
+                    for kk in range(V):
+                        lines.append(f"const {T} d{tag}_{kk} = __ldg(pd{tag} + {kk});")
+            return f"d{v}_{_m(cur[1])}_{k}"
 
         def val(v, cur, k) -> str:
             key = (v, cur, k)
@@ -227,38 +314,32 @@ class StageEmitter:
             if op.realm == SCALAR:
                 memo[key] = f"s{v}"
                 return memo[key]
+            if v in self.uniform:
+                self.uniform_used[v] = None
+                memo[key] = f"u{v}"
+                return memo[key]
             if v in mats and not (v in target_set and cur == (0, 0)):
-                if v in local_mats and cur == (0, 0):
-                    e = memo[(v, (0, 0), k)]
-                else:
-                    e = ring_read(v, cur, k)
+                e = ring_read(v, cur, k)
                 memo[key] = e
                 return e
             if op.kind == "Load":
                 inp = self.st.inputs[v]
-                if inp.via_smem:
-                    e = ring_read(v, cur, k)
-                else:
-                    assert cur == (0, 0)
-                    e = f"d{v}_{k}"
-                    if (v, "direct") not in memo:
-                        memo[(v, "direct")] = "1"
-                        lines.extend(self.direct_load(v, row))
+                e = ring_read(v, cur, k) if inp.via_smem else direct_read(v, cur, k)
                 memo[key] = e
                 return e
-            if op.kind == "Imm":
-                e = c_imm(op.inst.arg, op.ctype)
-            elif op.kind == "Broadcast":
-                e = f"s{op.args[0]}"
-            elif op.kind == "LoadIndex":
+            if op.kind == "LoadIndex":
                 ax = op.inst.arg
                 nm = f"ix{ax}_{_cur(cur)}_{k}"
                 if (nm, "def") not in memo:
                     memo[(nm, "def")] = "1"
                     if ax == 0:
-                        lines.append(f"const int {nm} = g.cyc_x ? om_wrap(tc + {k} + ({cur[0]}) - g.xorg, g.nx) : (tc + {k} + ({cur[0]}) - g.xorg);")
+                        hn = f"hix_{_m(cur[0])}_{k}"
+                        if hn not in self.pre_names:
+                            self.pre_names.add(hn)
+                            self.pre.append(f"const int {hn} = g.cyc_x ? om_wrap(tc + {k} + ({cur[0]}) - g.xorg, g.nx) : (tc + {k} + ({cur[0]}) - g.xorg);")
+                        lines.append(f"const int {nm} = {hn};")
                     else:
-                        lines.append(f"const int {nm} = g.cyc_y ? om_wrap({row} + ({cur[1]}) - g.yorg + g.y0, g.ny) : ({row} + ({cur[1]}) - g.yorg + g.y0);")
+                        lines.append(f"const int {nm} = g.cyc_y ? om_wrap(row + ({cur[1]}) - g.yorg + g.y0, g.ny) : (row + ({cur[1]}) - g.yorg + g.y0);")
                 e = f"(({T}){nm})"
             elif op.kind == "LoadSize":
                 e = f"(({T}){'g.nx' if op.inst.arg == 0 else 'g.ny'})"
@@ -269,7 +350,7 @@ class StageEmitter:
                 return e
             elif op.kind == "Arith":
                 args = [val(a, cur, k) for a in op.args]
-                e = arith_expr(op, args)
+                e = self.arith(op, args)
             else:
                 raise NotImplementedError(op.kind)
             nm = f"v{v}_{_cur(cur)}_{k}"
@@ -281,27 +362,13 @@ class StageEmitter:
         for t in sorted(targets):
             for k in range(V):
                 result[(t, k)] = val(t, (0, 0), k)
-            if t in mats:
-                local_mats[t] = None
         return lines, result
-
-    def direct_load(self, v, row) -> List[str]:
-        V = self.V
-        T = self.T(v)
-        sidx = self.static_of[v]
-        ls = [f"{T} " + ", ".join(f"d{v}_{k} = 0" for k in range(V)) + ";"]
-        ls.append(f"if ({row} >= 0 && {row} < g.rows) {{")
-        ls.append(f"  const {T}* __restrict__ p = in{sidx} + (size_t){row} * g.pitch;")
-        for k in range(V):
-            ls.append(f"  if (tc + {k} >= 0 && tc + {k} < g.pitch) d{v}_{k} = __ldg(p + tc + {k});")
-        ls.append("}")
-        return ls
 
     # ---- whole kernel ---------------------------------------------------------------------------
     def kernel(self) -> str:
         st, V, NT = self.st, self.V, self.NT
         om = self.om
-        E = self.emit
+        self.pre_names = set()
         in_statics = sorted({i.static_idx for i in st.inputs.values()})
         out_statics = [s for (s, _v) in st.store_targets]
         sv = om.setup.static_values
@@ -311,89 +378,101 @@ class StageEmitter:
         for s in out_statics:
             params.append(f"{CPP_TYPE[sv[s].namee.type]}* __restrict__ out{s}")
         params += ["om_slot_t* __restrict__ sc", "unsigned* __restrict__ red_counter", "om_slot_t* __restrict__ red_partials"]
+        mlx, mhx = self.margin_lo[0], self.margin_hi[0]
+        warm = st.warmup
+        has_ring_in = bool(self.ring_inputs)
+        lead = warm + (PF if has_ring_in else 0)
+
+        # ---- loop body first (it registers slot counters, hoisted values, uniform nodes) -------
+        B: List[str] = []
+        if has_ring_in:
+            B.append("// stage the next input rows (LDGSTS); the apron rows around every array make bounds checks unnecessary")
+            for i in self.ring_inputs:
+                v = i.vid
+                T = self.T(v)
+                nb = TYPE_BYTES[i.ctype] * V
+                so = self.slot_off(self.depth[v], i.lag + PF)
+                self.pre.append(f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + PF}) * g.pitch + tc;   // advances one row per iteration")
+                B.append(f"om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
+                if self.PL:
+                    B.append(f"if (tid < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + tid * V], src{v} - PL, {nb});")
+                if self.PR:
+                    B.append(f"if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
+                B.append(f"src{v} += g.pitch;")
+            B.append("om_cp_async_commit();")
+            B.append(f"om_cp_async_wait<{PF}>();")
+        B.append("__syncthreads();")
+        nph = max(len(st.phases), st.out_level)
+        for lvl in range(1, nph + 1):
+            if lvl > 1:
+                B.append("__syncthreads();")
+            mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
+            lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
+            for a in lags:
+                grp = [m for m in mats_here if st.mats[m].lag == a]
+                early = min(st.mats[m].early for m in grp)
+                B.append(f"if (j >= r0 - {-early}) {{   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
+                B.append(f"  const int row = j + {a};")
+                lines, res = self.scope(grp, a)
+                B += ["  " + l for l in lines]
+                for m in grp:
+                    so = self.slot_off(self.depth[m], a)
+                    T = self.T(m)
+                    vt = VEC_TYPE.get((T, V))
+                    if vt:
+                        B.append(f"  *reinterpret_cast<{vt}*>(&ring{m}[{so} + tb]) = make_{vt}({', '.join(res[(m, k)] for k in range(V))});")
+                    else:
+                        for k in range(V):
+                            B.append(f"  ring{m}[{so} + tb + {k}] = {res[(m, k)]};")
+                B.append("}")
+            if lvl == st.out_level:
+                B += self.emit_out()
+
+        # ---- assemble -----------------------------------------------------------------------------
+        L: List[str] = []
+        E = L.append
         E(f"// stage {self.idx} of kernel `{self.ks.name}` (reduce level {st.level}): "
           f"{len(st.mats)} shared-memory rings for intermediates, {len(self.ring_inputs)} for inputs, "
-          f"{len(st.phases)} phase(s), warm-up {st.warmup} rows")
-        E(f"__global__ void __launch_bounds__({NT}) {self.name}_kernel({', '.join(params)}) {{")
+          f"{nph} phase(s), warm-up {st.warmup} rows, {V} cell(s) per thread")
+        minb = int(_os.environ.get("OM_MINBLOCKS", "0")) if not st.mats else 0
+        lb = f"__launch_bounds__({NT}, {minb})" if minb else f"__launch_bounds__({NT})"
+        E(f"__global__ void {lb} {self.name}_kernel({', '.join(params)}) {{")
         E(f"  constexpr int V = {V}, NT = {NT}, HL = {self.HL}, PL = {self.PL}, RW = {self.RW}, W_OUT = {self.W_OUT};")
         E("  const int tid = threadIdx.x;")
+        E("  const int tb = PL + tid * V;                           // this thread's element offset inside a ring row")
         E("  OM_DYNAMIC_SMEM(om_smem);")
         off = 0
         for v, d in self.depth.items():
             off = _ru(off, 16)
             E(f"  {self.T(v)}* const ring{v} = reinterpret_cast<{self.T(v)}*>(om_smem + {off});  // {d} rows")
             off += d * self.RW * TYPE_BYTES[self.ops[v].ctype]
-        # column geometry: memory box [cx0, cx1), strips start at a V-aligned column
-        mlx, mhx = self.margin_lo[0], self.margin_hi[0]
-        mly, mhy = self.margin_lo[1], self.margin_hi[1]
-        E(f"  const int cx0 = g.xorg - {mlx}, cx1 = g.xorg + g.nx + {mhx};")
+        E(f"  const int cx0 = g.xorg - {mlx}, cx1 = g.xorg + g.nx + {mhx};   // columns of the reference memory box")
         E("  const int cA = (cx0 / V) * V;")
-        E("  const int strip_lo = cA + blockIdx.x * W_OUT;          // first output column of this CTA")
+        E("  const int strip_lo = cA + blockIdx.x * W_OUT;            // first output column of this CTA")
         E("  const int tc = strip_lo - HL + tid * V;                  // first column of this thread")
         E("  const int r0 = g.own_r0 + blockIdx.y * g.chunk_rows;")
         E("  const int r1 = min(r0 + g.chunk_rows, g.own_r1);")
-        # uniform scalars
-        roots = list(dict.fromkeys(st.scalar_roots))
-        for l in self.scalar_code(roots):
+        E(f"  const int jbeg = r0 - {lead};")
+        for l in self.scalar_code(list(dict.fromkeys(st.scalar_roots))):
             E("  " + l)
-        # reduce accumulators
+        for l in self.uniform_code():
+            E("  " + l)
+        for l in self.pre:
+            E("  " + l)
         for (v, rop, slot) in st.reduce_targets:
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             E(f"  {T} acc{v} = {ident};")
-        warm = st.warmup
-        has_ring_in = bool(self.ring_inputs)
-        lead = warm + (PF if has_ring_in else 0)
-        E(f"  for (int j = r0 - {lead}; j < r1; ++j) {{")
-        if has_ring_in:
-            E("    // ---- stage the next input rows (LDGSTS); off-array cells are zero-filled")
-            for i in self.ring_inputs:
-                v = i.vid
-                T = self.T(v)
-                B = TYPE_BYTES[i.ctype] * V
-                E(f"    {{ const int rr = j + {i.lag + PF};")
-                E(f"      const int sl = (rr + {1 << 20} * {self.depth[v]}) % {self.depth[v]};")
-                E(f"      const bool rok = (rr >= 0) && (rr < g.rows);")
-                E(f"      const {T}* __restrict__ src = in{i.static_idx} + (size_t)(rok ? rr : 0) * g.pitch;")
-                E(f"      {{ const bool ok = rok && (tc >= 0) && (tc + V <= g.pitch);")
-                E(f"        om_cp_async<{B}>(&ring{v}[sl * RW + PL + tid * V], src + (ok ? tc : 0), ok ? {B} : 0); }}")
-                if self.PL:
-                    E(f"      if (tid < {self.PL // V}) {{ const int c = strip_lo - HL - PL + tid * V; const bool ok = rok && (c >= 0) && (c + V <= g.pitch);")
-                    E(f"        om_cp_async<{B}>(&ring{v}[sl * RW + tid * V], src + (ok ? c : 0), ok ? {B} : 0); }}")
-                if self.PR:
-                    E(f"      if (tid < {self.PR // V}) {{ const int c = strip_lo - HL + NT * V + tid * V; const bool ok = rok && (c >= 0) && (c + V <= g.pitch);")
-                    E(f"        om_cp_async<{B}>(&ring{v}[sl * RW + PL + NT * V + tid * V], src + (ok ? c : 0), ok ? {B} : 0); }}")
-                E("    }")
-            E("    om_cp_async_commit();")
-            E(f"    om_cp_async_wait<{PF}>();")
-        E("    __syncthreads();")
-        nph = max(len(st.phases), st.out_level)
-        for lvl in range(1, nph + 1):
-            if lvl > 1:
-                E("    __syncthreads();")
-            mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
-            # scopes: MAT nodes sharing a lag share SSA values
-            lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
-            for a in lags:
-                grp = [m for m in mats_here if st.mats[m].lag == a]
-                early = min(st.mats[m].early for m in grp)
-                E(f"    if (j >= r0 - {-early}) {{   // phase {lvl}: rows j+{a} of {len(grp)} intermediate(s)")
-                E(f"      const int row = j + {a};")
-                lines, res = self.scope(grp, "row", False)
-                for l in lines:
-                    E("      " + l)
-                for m in grp:
-                    E(f"      {{ const int sl = (row + {1 << 20} * {self.depth[m]}) % {self.depth[m]};")
-                    for k in range(V):
-                        E(f"        ring{m}[sl * RW + PL + tid * V + {k}] = {res[(m, k)]};")
-                    E("      }")
-                E("    }")
-            if lvl == st.out_level:
-                self.emit_out()
+        for (d, c), nm in sorted(self.slotvars.items()):
+            E(f"  int {nm} = ((((jbeg + {c}) % {d}) + {d}) % {d}) * RW;")
+        E("  for (int j = jbeg; j < r1; ++j) {")
+        L += ["    " + l for l in B]
+        for (d, c), nm in sorted(self.slotvars.items()):
+            E(f"    {nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
         E("  }")
-        self.emit_reduce_epilogue()
+        L += self.emit_reduce_epilogue()
         E("}")
-        return "\n".join(self.lines)
+        return "\n".join(L)
 
     def type_max(self, v) -> str:
         return {"Int": "2147483647", "Float": "__int_as_float(0x7f800000)", "Double": "__longlong_as_double(0x7ff0000000000000LL)",
@@ -414,89 +493,110 @@ class StageEmitter:
         hi = tuple(hi) + (0,) * (2 - len(hi))
         return lo[0], hi[0], lo[1], hi[1]
 
-    def emit_out(self):
-        st, V, E = self.st, self.V, self.emit
-        targets = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
-        targets = list(dict.fromkeys(targets))
-        mlx, mhx = self.margin_lo[0], self.margin_hi[0]
+    def emit_out(self, row_expr: str = "j", guard: str = "j >= r0") -> List[str]:
+        """Stores + reduce accumulation for one output row.  The common case (all V lanes of the thread
+        inside the strip's output range, no ghost cell to mirror) is a single predicated vector store;
+        per-lane predicates are only evaluated on the rare partial-vector path."""
+        st, V = self.st, self.V
+        B: List[str] = []
+        targets = list(dict.fromkeys([v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]))
         mly, mhy = self.margin_lo[1], self.margin_hi[1]
-        E("    if (j >= r0) {   // OUT: stores and reduce accumulation for row j")
-        E("      const int row = j;")
-        lines, res = self.scope(targets, "row", True)
-        for l in lines:
-            E("      " + l)
-        # global memory-box row of this device row (reference memory coordinates)
-        E(f"      const int gmy = row - g.yorg + g.y0 + {mly};")
-        E(f"      const int memy = g.ny + {mly + mhy};")
-        for k in range(V):
-            E(f"      const bool in{k} = (tc + {k} >= max(cx0, strip_lo)) && (tc + {k} < min(cx1, strip_lo + W_OUT));")
-        all_in = " && ".join(f"in{k}" for k in range(V))
+
+        def P(line):
+            if line not in self.pre:
+                self.pre.append(line)
+        P("const int out_lo = max(cx0, strip_lo), out_hi = min(cx1, strip_lo + W_OUT);   // this CTA's output columns")
+        P("const bool li_all = (tc >= out_lo) && (tc + V <= out_hi);                     // whole vector inside")
+        P("const bool li_any = (tc + V > out_lo) && (tc < out_hi);")
+        P("const bool edge_x = g.cyc_x && (strip_lo < g.xorg + g.gx_hi || strip_lo + W_OUT > g.xorg + g.nx - g.gx_lo);")
+        P("const bool edge_y = g.wrap_y_local && (r0 < g.yorg + g.gy_hi || r1 > g.yorg + g.nyl - g.gy_lo);")
+        P("const bool edge_any = edge_x || edge_y;   // this CTA writes cells that have a ghost copy")
+        B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
+        B.append(f"  const int row = {row_expr};")
+        lines, res = self.scope(targets, 0)
+        B += ["  " + l for l in lines]
+        need_gmy = False
         for v in targets:
             lbx, ubx, lby, uby = self.valid_box(v)
             T = self.T(v)
-            E(f"      const bool vy{v} = (gmy >= {lby}) && (gmy < memy - {uby});")
+            conds_row = []
+            if lby or uby:
+                need_gmy = True
+                conds_row.append(f"(gmy >= {lby}) && (gmy < memy - {uby})")
             for k in range(V):
-                E(f"      const {T} o{v}_{k} = (vy{v} && (tc + {k} >= cx0 + {lbx}) && (tc + {k} < cx1 - {ubx})) ? {res[(v, k)]} : ({T})0;")
+                conds = list(conds_row)
+                if lbx or ubx:
+                    hn = f"vx{v}_{k}"
+                    P(f"const bool {hn} = (tc + {k} >= cx0 + {lbx}) && (tc + {k} < cx1 - {ubx});")
+                    conds.append(hn)
+                if conds:   # cells of the memory box outside the Valid region are never written by the reference: they stay 0
+                    B.append(f"  const {T} o{v}_{k} = ({' && '.join(conds)}) ? {res[(v, k)]} : ({T})0;")
+                else:
+                    B.append(f"  const {T} o{v}_{k} = {res[(v, k)]};")
+        if need_gmy:
+            idx = B.index(f"  const int row = {row_expr};")
+            B.insert(idx + 1, f"  const int gmy = row - g.yorg + g.y0 + {mly}; const int memy = g.ny + {mly + mhy};   // row in the reference memory box")
         for (s, v) in st.store_targets:
             T = self.T(v)
-            bytes_ = TYPE_BYTES[self.ops[v].ctype] * V
-            E(f"      {{ {T}* __restrict__ p = out{s} + (size_t)row * g.pitch + tc;")
-            vt = None
-            if V > 1 and bytes_ == 16:
-                vt = {"int": "int4", "float": "float4", "double": "double2"}.get(T)
-            elif V > 1 and bytes_ == 8:
-                vt = {"int": "int2", "float": "float2"}.get(T)
+            vt = VEC_TYPE.get((T, V))
+            P(f"{T}* __restrict__ po{s} = out{s} + (ptrdiff_t)r0 * g.pitch + tc;   // advances one row per output row")
+            B.append(f"  {{ {T}* __restrict__ p = po{s}; po{s} += g.pitch;")
             if vt:
-                comps = ", ".join(f"o{v}_{k}" for k in range(V))
-                E(f"        if ({all_in}) {{ *reinterpret_cast<{vt}*>(p) = make_{vt}({comps}); }}")
-                E("        else {")
+                B.append(f"    if (li_all) {{ *reinterpret_cast<{vt}*>(p) = make_{vt}({', '.join(f'o{v}_{k}' for k in range(V))}); }}")
+                B.append("    else if (li_any) {")
                 for k in range(V):
-                    E(f"          if (in{k}) p[{k}] = o{v}_{k};")
-                E("        }")
+                    B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = o{v}_{k};")
+                B.append("    }")
             else:
                 for k in range(V):
-                    E(f"        if (in{k}) p[{k}] = o{v}_{k};")
-            # fused ghost-cell writes for Cyclic axes (the wrap the reference computes with % per read,
-            # PlanTrans.hs:477-484, is materialised once per written cell here)
-            E("        const bool ex = g.cyc_x && (strip_lo < g.xorg + g.gx_hi || strip_lo + W_OUT > g.xorg + g.nx - g.gx_lo);")
-            E("        const bool ey = g.wrap_y_local && (row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo);")
-            E("        if (ex || ey) {")
+                    B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = o{v}_{k};")
+            # fused ghost-cell writes for Cyclic axes: the wrap the reference evaluates with % on every
+            # read (PlanTrans.hs:477-484) is materialised once per written cell
+            B.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
             for k in range(V):
-                E(f"          if (in{k}) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
-                E("            const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
-                E("            const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
-                E(f"            if (dc) p[{k} + dc] = o{v}_{k};")
-                E(f"            if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
-                E(f"            if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
-                # a domain narrower than the ghost width wraps from both sides
-                E("            if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[%d - g.nx] = o%d_%d;" % (k, v, k))
-                E("            if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[%d - (ptrdiff_t)g.nyl * g.pitch] = o%d_%d;" % (k, v, k))
-                E("          }")
-            E("        }")
-            E("      }")
+                B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
+                B.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
+                B.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
+                B.append(f"        if (dc) p[{k} + dc] = o{v}_{k};")
+                B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
+                B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
+                B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = o{v}_{k};   // domain narrower than the ghost width")
+                B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = o{v}_{k};")
+                B.append("      }")
+            B.append("    } }")
+            B.append("  }")
         for (v, rop, slot) in st.reduce_targets:
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
+            chain = f"acc{v}"
             for k in range(V):
-                E(f"      if (in{k}) acc{v} = {cls}::op(acc{v}, o{v}_{k});")
-        E("    }")
+                chain = f"{cls}::op({chain}, o{v}_{k})"
+            B.append(f"  if (li_all) {{ acc{v} = {chain}; }}")
+            B.append("  else if (li_any) {")
+            for k in range(V):
+                B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{v} = {cls}::op(acc{v}, o{v}_{k});")
+            B.append("  }")
+        B.append("}")
+        return B
 
-    def emit_reduce_epilogue(self):
-        st, E, NT = self.st, self.emit, self.NT
+    def emit_reduce_epilogue(self) -> List[str]:
+        st = self.st
+        L: List[str] = []
         if not st.reduce_targets:
-            return
-        E("  // ---- block reduce -> per-CTA partial -> last CTA folds all partials (om_runtime.cuh)")
+            return L
+        L.append("  // block reduce -> per-CTA partial -> the last CTA folds all partials (om_runtime.cuh)")
         for t, (v, rop, slot) in enumerate(st.reduce_targets):
             T = self.T(v)
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
-            E(f"  {{ __shared__ {T} red{v}[32]; {T} result;")
-            E(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y);")
-            E(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{v}, {ident}, partials, red_counter + {t}, red{v}, result)) {{")
-            E(f"      om_slot_store<{T}>(sc, {slot}, result);")
-            E(f"      red_counter[{t}] = 0u;")
-            E("    }")
-            E("    __syncthreads();")
-            E("  }")
+            L.append(f"  {{ __shared__ {T} red{v}[32]; {T} result;")
+            L.append(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y);")
+            L.append(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{v}, {ident}, partials, red_counter + {t}, red{v}, result)) {{")
+            L.append(f"      om_slot_store<{T}>(sc, {slot}, result);")
+            L.append(f"      red_counter[{t}] = 0u;")
+            L.append("    }")
+            L.append("    __syncthreads();")
+            L.append("  }")
+        return L
 
     def launcher(self) -> str:
         st = self.st
@@ -519,11 +619,18 @@ class StageEmitter:
         L.append("  const int nrows = g->own_r1 - g->own_r0;")
         L.append("  if (nrows <= 0 || strips <= 0) return 0;")
         L.append("  const int chunks = (nrows + g->chunk_rows - 1) / g->chunk_rows;")
-        L.append(f"  static bool attr_set = false;")
+        L.append("  static bool attr_set = false;")
         L.append(f"  if (!attr_set) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; attr_set = true; }}")
         L.append(f"  OM_LAUNCH({self.name}_kernel, dim3(strips, chunks), {self.NT}, {smem}, (cudaStream_t)stream, {', '.join(args)});")
         L.append("  OM_CUDA_CHECK_LAUNCH();")
         L.append("  return 0;")
+        L.append("}")
+        L.append(f"// resident CTAs per SM for this stage (the host sizes the grid to whole waves with it)")
+        L.append(f'extern "C" int {self.name}_occupancy(void) {{')
+        L.append(f"  int n = 0;")
+        L.append(f"  if (cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}) != cudaSuccess) return -1;")
+        L.append(f"  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, {self.name}_kernel, {self.NT}, {smem}) != cudaSuccess) return -1;")
+        L.append("  return n;")
         L.append("}")
         return "\n".join(L)
 
@@ -560,5 +667,5 @@ def pick_vnt(om: OM, st: Stage, ks: KernelSchedule) -> Tuple[int, int]:
     types += [ks.ops[v].ctype for (v, _o, _k) in st.reduce_targets]
     width = max([TYPE_BYTES[t] for t in types] + [4])
     if st.mats:
-        return (1, 256)
-    return (16 // width if width <= 8 else 1, 128)
+        return (1, int(_os.environ.get("OM_NT_HEAVY", "256")))
+    return (16 // width if width <= 8 else 1, int(_os.environ.get("OM_NT", "128")))

@@ -293,7 +293,9 @@ class StageBuilder:
                                      early=early[b], rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"])
             else:
                 op = ops[b]
-                via = any(c != (0, 0) for (_n, c) in d["uses"]) or d["depth"] > 1
+                # through shared memory only when another thread's columns are read; same-column reads
+                # at several rows are plain (L1/L2-resident) global loads
+                via = any(c[0] != 0 for (_n, c) in d["uses"])
                 st.inputs[b] = InputArr(static_idx=op.inst.arg, vid=b, ctype=op.ctype, lag=lag[b], depth=d["depth"],
                                         via_smem=via, xlo=xlo[b], xhi=xhi[b], early=early[b],
                                         rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"])

@@ -31,6 +31,7 @@ TORCH_TYPE = {"Int": torch.int32, "Float": torch.float32, "Double": torch.float6
               "Integer": torch.int64}
 NP_TYPE = {"Int": np.int32, "Float": np.float32, "Double": np.float64, "Bool": np.bool_, "Integer": np.int64}
 SM_COUNT = 148
+APRON = 16   # = APRON_ROWS of generator/b200/cuda.py
 
 
 class OmGeom(ctypes.Structure):
@@ -94,13 +95,18 @@ class Machine:
         # storage
         self.statics = desc["statics"]
         self.index = {s["name"]: i for i, s in enumerate(self.statics)}
+        self._storage: List[torch.Tensor] = []
         self.cur: List[Optional[torch.Tensor]] = []
         self.alt: List[Optional[torch.Tensor]] = []
         for s in self.statics:
             if s["realm"] == "Array":
                 t = TORCH_TYPE[s["type"]]
-                self.cur.append(torch.zeros((self.rows, self.pitch), dtype=t, device=self.device))
-                self.alt.append(torch.zeros((self.rows, self.pitch), dtype=t, device=self.device))
+                # APRON rows of zero-initialised slack above and below: the kernels read a few rows
+                # beyond the slab while filling their pipelines and do not bounds-check (C-ABI contract)
+                for lst in (self.cur, self.alt):
+                    full = torch.zeros((self.rows + 2 * APRON, self.pitch), dtype=t, device=self.device)
+                    self._storage.append(full)
+                    lst.append(full[APRON:APRON + self.rows])
             else:
                 self.cur.append(None)
                 self.alt.append(None)
@@ -157,11 +163,23 @@ class Machine:
             return g
         nrows = self.own_r1 - self.own_r0
         strips = max(1, -(-(self.cx1 - (self.cx0 // st["V"]) * st["V"]) // st["w_out"]))
-        per_sm = max(1, min(16, (220 * 1024) // max(st["smem"], 1), 2048 // st["NT"]))
-        want = SM_COUNT * per_sm * 2
-        chunks = max(1, min(want // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
-        chunks = max(1, chunks)
+        occ = getattr(self.lib, st["symbol"] + "_occupancy")()
+        if occ <= 0:
+            raise RuntimeError(f"{st['symbol']}: occupancy query failed ({occ})")
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 4
+        # heavy (shared-memory) stages: one full wave of equally long CTAs; light streaming stages:
+        # a few waves of shorter CTAs so that the tail of the grid does not idle SMs
+        import os
+        heavy = st["phases"] > 1 or st["smem"] > 48 * 1024
+        if heavy:
+            chunks = max(1, min((sms * occ) // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
+        else:
+            # measured on B200 (profiles/r1_life_sweep.txt): ~32-row chunks keep the set of concurrently
+            # streamed rows compact and balance the tail; the extra warm-up rows are L2 hits
+            chunks = max(1, nrows // 32)
         chunk_rows = -(-nrows // chunks)
+        if os.environ.get("OM_CHUNK_ROWS"):
+            chunk_rows = max(1, int(os.environ["OM_CHUNK_ROWS"]))
         g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
                    cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),

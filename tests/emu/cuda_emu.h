@@ -37,6 +37,7 @@ static const cudaError_t cudaSuccess = 0;
 static const int cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
 template <class F> static cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <class F> static cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
@@ -74,6 +75,16 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
   emu_block->warp_bar[wid]->arrive_and_wait();
   T r = v;
   if (lane + d < 32) memcpy(&r, emu_block->xchg[wid][lane + d], sizeof(T));
+  emu_block->warp_bar[wid]->arrive_and_wait();
+  return r;
+}
+
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  memcpy(emu_block->xchg[wid][lane], &v, sizeof(T));
+  emu_block->warp_bar[wid]->arrive_and_wait();
+  T r = v;
+  if (lane - d >= 0) memcpy(&r, emu_block->xchg[wid][lane - d], sizeof(T));
   emu_block->warp_bar[wid]->arrive_and_wait();
   return r;
 }

@@ -1,0 +1,21 @@
+"""Profiling driver (run under ncu on the GPU box): a few proceed() steps of one workload."""
+import sys
+import torch
+from paraiso_b200.machines import hydro_machine, hydro_set_params, life_machine, life_seed
+
+wl = sys.argv[1]
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+if wl == "life":
+    size = (16384, 16384)
+    m = life_machine(size)
+    m.call("init")
+    m.set("cell", life_seed(size[0], 0, size[1]))
+else:
+    size = (4096, 4096)
+    m = hydro_machine(size, fmad=(len(sys.argv) > 3 and sys.argv[3] == "fma"))
+    hydro_set_params(m, size)
+    m.call("init")
+for _ in range(steps):
+    m.call("proceed")
+torch.cuda.synchronize()
+print("done", wl, steps)
