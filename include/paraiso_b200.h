@@ -1,0 +1,40 @@
+/* paraiso_b200.h — the C ABI between a Paraiso host class and the B200 kernels.
+ *
+ * What it replaces.  The reference's CUDA flavour emits one translation unit in which the member function
+ * of every subkernel launches its `__global__` helper directly:
+ *     Language/Paraiso/Generator/PlanTrans.hs:295-314   (the `<sub>_inner` kernel: flat grid-stride loop)
+ *     Language/Paraiso/Generator/PlanTrans.hs:318-343   (`<sub>_inner<<<grid, block>>>(raw pointers...)`)
+ *     Language/Paraiso/Generator/PlanTrans.hs:225-258   (kernel driver: subkernel calls, then `static = manifest` copies)
+ *     Language/Paraiso/Generator/PlanTrans.hs:719-720   (om_reduce_* via Thrust, result returned to the host)
+ * There is no FFI in the reference.  This header is the boundary a maintainer binds instead: one
+ * `extern "C"` launcher per fused GPU stage of every OM kernel, plain pointers and ints only.
+ *
+ * Per machine `<Name>` the generator emits `<Name>_abi.h` (copied here as om_<Name>_abi.h) declaring
+ *     int om_<Name>_abi_version(void);
+ *     int om_<Name>_<kernel>_stage<k>(const OmGeomC* g, void* const* cur, void* const* alt,
+ *                                     void* sc, void* scratch, void* stream);
+ *     int om_<Name>_<kernel>_stage<k>_occupancy(void);
+ *     int om_<Name>_<kernel>_scalars(const OmGeomC* g, void* sc, void* stream);
+ *
+ * Calling convention
+ *   g        geometry of this rank's slab (sizes are run-time values; margins / boundary kinds are baked in)
+ *   cur/alt  arrays of device pointers indexed by static-variable index; a stage reads `cur[i]` and writes
+ *            `alt[i]`; after all stages of an OM kernel the host swaps cur/alt of every stored array
+ *            (the reference's store-after-compute semantics, PlanTrans.hs:228, without the copy)
+ *   sc       device scalar slots, 8 bytes each: slot i < nstatics is static variable i (Scalar realm),
+ *            the following slots hold Reduce results
+ *   scratch  >= 256 + 8 * CTAs * reduces bytes of device memory, zeroed once at creation
+ *   stream   cudaStream_t
+ *   return   0, or the cudaError_t of the failed launch; nothing throws across the boundary
+ *
+ * Memory contract: every array is `rows` x `pitch` elements, row-major, axis 0 fastest
+ * (PlanTrans.hs:449-454), interior cell (0, y0) at (row yorg, column xorg), ghost / margin cells around
+ * it, and OM_APRON_ROWS zero-initialised rows allocated above row 0 and below row rows-1 (kernels do not
+ * bounds-check their pipeline fill).  `pitch` is a multiple of 32 elements, `xorg` a multiple of 32.
+ * On Cyclic axes the ghost cells of an array must be valid before a stage reads it; stages keep them valid
+ * for the arrays they write (x always; y when wrap_y_local), the host refreshes them after host writes and,
+ * with several ranks, exchanges the y ghost rows.
+ */
+#pragma once
+#include "om_Life_abi.h"
+#include "om_Hydro_abi.h"

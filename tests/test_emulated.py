@@ -1,0 +1,93 @@
+"""The generated CUDA kernels, compiled for host threads (tests/emu), against the oracle.  This checks the
+schedule logic (rings, lags, phases, ghost writes, reductions, both skeletons) on a machine without a GPU;
+the GPU parity tests proper are in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.cpu import OracleMachine
+from paraiso_b200.examples.helloworld import helloworld_om, helloworld_setup
+from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+from paraiso_b200.examples.life import life_om, life_setup
+from paraiso_b200.examples.shiftexample import shiftexample_om, shiftexample_setup
+from paraiso_b200.runtime import Machine
+from tests.emu.build_emu import build_emulated
+
+
+def _life(size, steps, mode):
+    os.environ["OM_MODE"] = mode
+    try:
+        desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag=f"Life_{mode}")
+    finally:
+        os.environ.pop("OM_MODE")
+    m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+    o = OracleMachine(life_setup("master", size=size), life_om("master"))
+    init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
+    m.call("init"); o.call("init")
+    m.set("cell", init); o.interior("cell")[...] = init
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+        assert np.array_equal(m.get("cell"), o.interior("cell")), t
+        assert int(m.scalar("population")) == int(o.scalar("population")[0])
+    assert int(m.scalar("generation")) == steps
+
+
+@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37)])
+def test_life_ring_skeleton(size):
+    _life(size, 4, "ring")
+
+
+@pytest.mark.parametrize("size", [(80, 48), (513, 40)])
+def test_life_register_streaming_skeleton(size):
+    _life(size, 4, "stream")
+
+
+def test_hydro_master_double_bit_identical():
+    size = (64, 48)
+    desc, so = build_emulated(hydro_setup(size), hydro_om("master"))
+    m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+    o = OracleMachine(hydro_setup(size), hydro_om("master"))
+    for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+        m.set_scalar(k, v)
+        o.scalar(k)[0] = v
+    m.call("init"); o.call("init")
+    names = ["density", "velocity0", "velocity1", "pressure"]
+    for n in names:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64))
+    for t in range(2):
+        m.call("proceed"); o.call("proceed")
+    for n in names:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
+    assert m.scalar("time") == o.scalar("time")[0]
+
+
+def test_helloworld_known_answer():
+    """examples/HelloWorld: table(x,y) = x*y on 10x20, total = 45*190 = 8550."""
+    desc, so = build_emulated(helloworld_setup(), helloworld_om(), tag="Hello")
+    m = Machine(desc, so, device="cpu", _emulated=True)
+    m.call("create")
+    t = m.get("table")
+    assert t.shape == (20, 10) and all(t[y, x] == x * y for x in range(10) for y in range(20))
+    assert int(m.scalar("total")) == 8550
+
+
+@pytest.mark.parametrize("cyclic", [False, True])
+def test_shiftexample_known_answer(cyclic):
+    """examples/ShiftExample: init; increment; calculate -> table[i] = 10000*t[i-1] + 100*t[i] + t[i+1], t[i] = i+1."""
+    s = shiftexample_setup(cyclic)
+    desc, so = build_emulated(s, shiftexample_om(), tag=f"Shift{cyclic}")
+    m = Machine(desc, so, device="cpu", _emulated=True)
+    for k in ("init", "increment", "calculate"):
+        m.call(k)
+    t = np.arange(1, 9)
+    if cyclic:
+        want = 10000 * np.roll(t, 1) + 100 * t + np.roll(t, -1)
+        got = m.get("table").ravel()
+    else:   # Open: margins hold loadIndex+1 too (index -1 -> 0, index 8 -> 9); only the interior is valid
+        tt = np.arange(0, 10)
+        want = 10000 * tt[:-2] + 100 * tt[1:-1] + tt[2:]
+        got = m.get("table").ravel()
+        assert list(m.get("table", with_margin=True).ravel()[[0, -1]]) == [0, 0]   # never written: stays 0
+    assert np.array_equal(got, want)
+    assert int(m.scalar("total")) == int(want.sum())

@@ -1,0 +1,95 @@
+"""world_size-2 runs of the slab-decomposed host path on CPU (gloo backend, emulated kernels):
+decomposition invariance — the 2-rank result is bit-identical to the 1-rank result — for the Cyclic ring
+(Life: halo rows + population all_reduce(sum)) and the Open chain (Hydro: halo rows + dt all_reduce(min))."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, which, size, steps, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from paraiso_b200.runtime import Machine
+    from tests.emu.build_emu import build_emulated
+    if which == "life":
+        from paraiso_b200.examples.life import life_om, life_setup
+        from paraiso_b200.machines import life_seed
+        desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring")
+        m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
+        m.call("init")
+        m.set("cell", life_seed(size[0], m.y0, m.nyl, nx_global=size[0]))
+        for _ in range(steps):
+            m.call("proceed")
+        ret[rank] = (m.y0, m.get("cell"), int(m.scalar("population")))
+    else:
+        from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+        from paraiso_b200.machines import hydro_set_params
+        desc, so = build_emulated(hydro_setup(size), hydro_om("master"))
+        m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
+        hydro_set_params(m, size)
+        m.call("init")
+        for _ in range(steps):
+            m.call("proceed")
+        ret[rank] = (m.y0, {n: m.get(n) for n in ("density", "velocity0", "velocity1", "pressure")}, float(m.scalar("time")))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(which, size, steps, world, port):
+    if world == 1:
+        ret = {}
+        # a 1-rank run needs no process group
+        sys.path.insert(0, ROOT)
+        from paraiso_b200.runtime import Machine
+        from tests.emu.build_emu import build_emulated
+        if which == "life":
+            from paraiso_b200.examples.life import life_om, life_setup
+            from paraiso_b200.machines import life_seed
+            desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring")
+            m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+            m.call("init")
+            m.set("cell", life_seed(size[0], 0, size[1]))
+            for _ in range(steps):
+                m.call("proceed")
+            return m.get("cell"), int(m.scalar("population"))
+        from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+        from paraiso_b200.machines import hydro_set_params
+        desc, so = build_emulated(hydro_setup(size), hydro_om("master"))
+        m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+        hydro_set_params(m, size)
+        m.call("init")
+        for _ in range(steps):
+            m.call("proceed")
+        return {n: m.get(n) for n in ("density", "velocity0", "velocity1", "pressure")}, float(m.scalar("time"))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, which, size, steps, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def test_life_two_ranks_equal_one_rank():
+    size, steps = (96, 50), 5
+    cell1, pop1 = _run("life", size, steps, 1, 0)
+    parts = _run("life", size, steps, 2, 29611)
+    cell2 = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=0)
+    assert np.array_equal(cell1, cell2)
+    assert all(p[2] == pop1 for p in parts)      # all_reduce(sum) gives every rank the global population
+
+
+def test_hydro_two_ranks_equal_one_rank():
+    size, steps = (40, 36), 3
+    f1, t1 = _run("hydro", size, steps, 1, 0)
+    parts = sorted(_run("hydro", size, steps, 2, 29613), key=lambda p: p[0])
+    for n in f1:
+        f2 = np.concatenate([p[1][n] for p in parts], axis=0)
+        assert np.array_equal(f1[n].view(np.uint64), f2.view(np.uint64)), n
+    assert all(p[2] == t1 for p in parts)        # all_reduce(min) of the CFL time step
