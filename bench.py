@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("OM_BENCH_WORKLOAD", "life"), choices=list(WORKLOADS))
     ap.add_argument("--fmad", action="store_true", help="Hydro: FMA-contracted build (within 1e-12, not bit-exact)")
+    ap.add_argument("--fast", action="store_true", help="Hydro: Setup.fast_math build (FMA + fast division/sqrt; within 1e-12)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +171,7 @@ def main():
         state = ["cell"]
         result_scalar = "population"
     else:
-        m = hydro_machine(gsize, fmad=args.fmad, **kw)
+        m = hydro_machine(gsize, fmad=args.fmad, fast=args.fast, **kw)
         hydro_set_params(m, gsize)
         m.call("init")
         state = ["density", "velocity0", "velocity1", "pressure"]
@@ -249,7 +250,8 @@ def main():
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": cfg_name, "global_grid": f"{gsize[0]}x{gsize[1]}", "per_gpu_grid": f"{m.nx}x{m.nyl}",
                            "decomposition": f"slab{world}" if world > 1 else "single", "l2": "state arrays are larger than L2 (no flush needed)",
-                           "build": "fmad=true" if args.fmad else "fmad=false (bit-exact vs reference C++)"},
+                           "build": ("fast_math (FMA, MUFU-seeded div/sqrt; within 1e-12 of the reference)" if args.fast else
+                                     "fmad=true" if args.fmad else "fmad=false (bit-exact vs reference C++)")},
                 "roofline": {"bound": "hbm", "kernel": kinfo["stages"][dom]["symbol"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_cell": alg_bytes, "kernel_ms": kms},

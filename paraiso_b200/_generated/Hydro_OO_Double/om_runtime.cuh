@@ -125,6 +125,46 @@ __device__ __forceinline__ bool om_block_reduce_finalize(T v, T identity, T* par
   return false;
 }
 
+// ---- fast-math build only (Setup.fast_math): division / square root without the IEEE slow path ------------
+// MUFU-seeded Newton iterations, then one residual correction: results are within 1 ulp of the correctly
+// rounded value for normal operands (no denormal / inf / NaN handling).  The default build does not use these:
+// it keeps IEEE division and square root so that results are bit-identical to the reference's C++.
+#ifndef OM_EMULATED_INTRINSICS
+__device__ __forceinline__ double om_frcp(double b) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));     // ~20 correct bits (MUFU.RCP64H)
+  double e = fma(-b, y, 1.0);
+  y = fma(y, e, y);                                          // ~40 bits
+  e = fma(-b, y, 1.0);
+  y = fma(y, e, y);                                          // full precision
+  return y;
+}
+__device__ __forceinline__ double om_frsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H
+  double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+#else
+static inline double om_frcp(double b) { return 1.0 / b; }
+static inline double om_frsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+__device__ __forceinline__ double om_fdiv_r(double a, double b, double rb) {   // a / b given rb ~ 1/b
+  const double q = a * rb;
+  return fma(fma(-b, q, a), rb, q);
+}
+__device__ __forceinline__ double om_fsqrt(double x) {
+  const double r = om_frsqrt(x);
+  const double s = x * r;
+  const double s2 = fma(fma(-s, s, x), 0.5 * r, s);
+  return x > 0.0 ? s2 : (x == 0.0 ? 0.0 : s);
+}
+__device__ __forceinline__ float om_frcp(float b) { return 1.0f / b; }
+__device__ __forceinline__ float om_fdiv_r(float a, float b, float rb) { (void)rb; return a / b; }
+__device__ __forceinline__ float om_fsqrt(float x) { return sqrtf(x); }
+
 // wrap an index into [0, n) assuming it is at most one period out of range
 __device__ __forceinline__ int om_wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
 

@@ -121,6 +121,7 @@ class StageEmitter:
         self.om, self.plan, self.ks, self.st, self.idx = om, plan, ks, st, stage_idx
         self.ops = ks.ops
         self.V, self.NT = V, NT
+        self.fast = bool(getattr(plan.setup, "fast_math", False))
         self.HL, self.HR = _ru(st.halo_x[0], V), _ru(st.halo_x[1], V)
         self.PL, self.PR = _ru(st.pad_x[0], V), _ru(st.pad_x[1], V)
         self.W_OUT = NT * V - self.HL - self.HR
@@ -351,6 +352,16 @@ class StageEmitter:
             elif op.kind == "Arith":
                 args = [val(a, cur, k) for a in op.args]
                 e = self.arith(op, args)
+                if self.fast and op.ctype == "Double" and op.inst.arg in ("Div", "Inv", "Sqrt") and e.count("*") == 0:
+                    if op.inst.arg == "Sqrt":
+                        e = f"om_fsqrt({args[0]})"
+                    else:
+                        den = args[-1]
+                        rk = ("rcp", den)
+                        if rk not in memo:     # one reciprocal per distinct denominator (and cursor / lane)
+                            memo[rk] = f"rc_{len([1 for q in memo if isinstance(q, tuple) and q and q[0] == 'rcp'])}_{k}"
+                            lines.append(f"const double {memo[rk]} = om_frcp({den});")
+                        e = memo[rk] if op.inst.arg == "Inv" else f"om_fdiv_r({args[0]}, {den}, {memo[rk]})"
             else:
                 raise NotImplementedError(op.kind)
             nm = f"v{v}_{_cur(cur)}_{k}"

@@ -15,9 +15,12 @@ def build_life(fmad: bool = False, verbose: bool = False):
     return build_machine(life_setup("master"), life_om("master"), tag=os.environ.get("OM_LIFE_TAG", "Life_CC"), fmad=fmad, verbose=verbose)
 
 
-def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False):
-    """examples/Hydro/HydroMain.hs (Open, Real = Double upstream)."""
-    return build_machine(hydro_setup(), hydro_om("master", real=real), tag=f"Hydro_OO_{real}", fmad=fmad, verbose=verbose)
+def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False, fast: bool = False):
+    """examples/Hydro/HydroMain.hs (Open, Real = Double upstream).  `fast` = Setup.fast_math (implies FMA)."""
+    setup = hydro_setup()
+    setup.fast_math = fast
+    return build_machine(setup, hydro_om("master", real=real), tag=f"Hydro_OO_{real}{'_fast' if fast else ''}",
+                         fmad=fmad or fast, verbose=verbose)
 
 
 def life_machine(size, device="cuda", **kw) -> Machine:
@@ -25,8 +28,8 @@ def life_machine(size, device="cuda", **kw) -> Machine:
     return Machine(desc, so, size=size, device=device, **kw)
 
 
-def hydro_machine(size, device="cuda", real: str = "Double", fmad: bool = False, **kw) -> Machine:
-    desc, so = build_hydro(real=real, fmad=fmad)
+def hydro_machine(size, device="cuda", real: str = "Double", fmad: bool = False, fast: bool = False, **kw) -> Machine:
+    desc, so = build_hydro(real=real, fmad=fmad, fast=fast)
     return Machine(desc, so, size=size, device=device, **kw)
 
 

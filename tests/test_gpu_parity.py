@@ -50,11 +50,11 @@ def test_life_init_pattern_gosper():
     assert int(m.scalar("population")) == int(ref.sum())
 
 
-def _hydro_pair(size, fmad=False):
+def _hydro_pair(size, fmad=False, fast=False):
     from oracle.cpu import OracleMachine
     from paraiso_b200.examples.hydro import hydro_om, hydro_setup
     from paraiso_b200.machines import hydro_machine, hydro_set_params
-    m = hydro_machine(size, fmad=fmad)
+    m = hydro_machine(size, fmad=fmad, fast=fast)
     o = OracleMachine(hydro_setup(size), hydro_om("master"), openmp=True, opt="-O2")
     hydro_set_params(m, size)
     for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
@@ -101,6 +101,22 @@ def test_hydro_fma_build_within_tolerance():
     for a, b in zip(ca, cb):
         scale = np.max(np.abs(b))
         assert np.max(np.abs(a - b)) / scale < 1e-12
+    assert abs(m.scalar("time") - o.scalar("time")[0]) / o.scalar("time")[0] < 1e-12
+
+
+@pytest.mark.parametrize("size,steps", [((512, 512), 20), ((1024, 1024), 20)])
+def test_hydro_fast_math_build_within_tolerance(size, steps):
+    """Setup.fast_math (FMA + MUFU-seeded division / sqrt with shared reciprocals): conserved variables and
+    `time` within 1e-12 relative of the oracle after 20 steps (north-star tolerance for double)."""
+    m, o = _hydro_pair(size, fast=True)
+    for n in NAMES:
+        m.set(n, o.array(n), with_margin=True)
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    ca = _conserved(lambda n: m.get(n))
+    cb = _conserved(lambda n: o.interior(n))
+    for a, b in zip(ca, cb):
+        assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 1e-12
     assert abs(m.scalar("time") - o.scalar("time")[0]) / o.scalar("time")[0] < 1e-12
 
 
