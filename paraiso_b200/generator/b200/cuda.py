@@ -141,6 +141,13 @@ class StageEmitter:
         self.uniform_used: Dict[int, None] = {}
         self.pre: List[str] = []                            # hoisted, before the row loop
         self.uniform = self._uniform_nodes()
+        self.window_u = None
+        # row-window mode: MAT-free stages whose inputs are staged in rings keep the stencil window in registers
+        self.window = (not st.mats) and bool(self.ring_inputs) and _os.environ.get("OM_WINDOW", "1") != "0"
+        if self.window:
+            self.wcmin = min(i.lag - i.depth + 1 for i in self.ring_inputs)
+            self.wcmax = max(i.lag for i in self.ring_inputs)
+            self.U = self.wcmax - self.wcmin + 1
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
         reach = st.warmup + PF + max([abs(i.lag) + i.depth for i in st.inputs.values()] + [0]) + 1
         assert reach <= APRON_ROWS, f"stage needs {reach} apron rows"
@@ -249,9 +256,13 @@ class StageEmitter:
         return out
 
     def staged_read(self, lines, ring_rd, lag, b, cur, k) -> str:
-        """Read staged value `b` (input or MAT) at cursor `cur` for lane k: shared-memory ring."""
+        """Read staged value `b` (input or MAT) at cursor `cur` for lane k: shared-memory ring, or — in
+        row-window mode — the register copy of that ring row (each ring row is read from shared memory
+        once, when it enters the stencil window, and reused by the following rows)."""
         V = self.V
         o = k + cur[0]
+        if self.window_u is not None:
+            return f"w{b}_{(self.window_u + cur[1] - self.wcmin) % self.U}_{_m(o)}"
         key = (b, cur[1], o)
         if key in ring_rd:
             return ring_rd[key]
@@ -395,15 +406,16 @@ class StageEmitter:
         lead = warm + (PF if has_ring_in else 0)
 
         # ---- loop body first (it registers slot counters, hoisted values, uniform nodes) -------
-        B: List[str] = []
-        if has_ring_in:
+        def stage_inputs(B, row_shift: int):
             B.append("// stage the next input rows (LDGSTS); the apron rows around every array make bounds checks unnecessary")
             for i in self.ring_inputs:
                 v = i.vid
                 T = self.T(v)
                 nb = TYPE_BYTES[i.ctype] * V
-                so = self.slot_off(self.depth[v], i.lag + PF)
-                self.pre.append(f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + PF}) * g.pitch + tc;   // advances one row per iteration")
+                so = self.slot_off(self.depth[v], i.lag + PF + row_shift)
+                ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + PF}) * g.pitch + tc;   // advances one row per staged row"
+                if ln not in self.pre:
+                    self.pre.append(ln)
                 B.append(f"om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
                 if self.PL:
                     B.append(f"if (tid < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + tid * V], src{v} - PL, {nb});")
@@ -412,32 +424,68 @@ class StageEmitter:
                 B.append(f"src{v} += g.pitch;")
             B.append("om_cp_async_commit();")
             B.append(f"om_cp_async_wait<{PF}>();")
-        B.append("__syncthreads();")
+
         nph = max(len(st.phases), st.out_level)
-        for lvl in range(1, nph + 1):
-            if lvl > 1:
+        bodies: List[List[str]] = []
+        if self.window:
+            # one unrolled body per window row: the register sets rotate by renaming
+            wregs: Dict[str, str] = {}
+            for u in range(self.U):
+                self.window_u = u
+                B: List[str] = []
+                stage_inputs(B, 0)
                 B.append("__syncthreads();")
-            mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
-            lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
-            for a in lags:
-                grp = [m for m in mats_here if st.mats[m].lag == a]
-                early = min(st.mats[m].early for m in grp)
-                B.append(f"if (j >= r0 - {-early}) {{   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
-                B.append(f"  const int row = j + {a};")
-                lines, res = self.scope(grp, a)
-                B += ["  " + l for l in lines]
-                for m in grp:
-                    so = self.slot_off(self.depth[m], a)
-                    T = self.T(m)
+                B.append("// the row that enters the stencil window: shared memory -> registers, once")
+                for i in self.ring_inputs:
+                    b, T = i.vid, self.T(i.vid)
+                    so = self.slot_off(self.depth[b], i.lag)
+                    sset = (u + i.lag - self.wcmin) % self.U
                     vt = VEC_TYPE.get((T, V))
+                    names = [f"w{b}_{sset}_{_m(o)}" for o in range(-i.rd_xlo, V + i.rd_xhi)]
+                    for n_ in names:
+                        wregs[n_] = T
                     if vt:
-                        B.append(f"  *reinterpret_cast<{vt}*>(&ring{m}[{so} + tb]) = make_{vt}({', '.join(res[(m, k)] for k in range(V))});")
+                        B.append(f"{{ const {vt} q = *reinterpret_cast<const {vt}*>(&ring{b}[{so} + tb]); " +
+                                 " ".join(f"w{b}_{sset}_{kk} = q.{'xyzw'[kk]};" for kk in range(V)) + " }")
                     else:
-                        for k in range(V):
-                            B.append(f"  ring{m}[{so} + tb + {k}] = {res[(m, k)]};")
-                B.append("}")
-            if lvl == st.out_level:
-                B += self.emit_out()
+                        for kk in range(V):
+                            B.append(f"w{b}_{sset}_{kk} = ring{b}[{so} + tb + {kk}];")
+                    for o in list(range(-i.rd_xlo, 0)) + list(range(V, V + i.rd_xhi)):
+                        B.append(f"w{b}_{sset}_{_m(o)} = ring{b}[{so} + tb + ({o})];")
+                B += self.emit_out(row_expr=f"j + {u}", guard=f"j + {u} >= r0")
+                bodies.append(B)
+            self.window_u = None
+            self.wregs = wregs
+        else:
+            B = []
+            if has_ring_in:
+                stage_inputs(B, 0)
+            B.append("__syncthreads();")
+            for lvl in range(1, nph + 1):
+                if lvl > 1:
+                    B.append("__syncthreads();")
+                mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
+                lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
+                for a in lags:
+                    grp = [m for m in mats_here if st.mats[m].lag == a]
+                    early = min(st.mats[m].early for m in grp)
+                    B.append(f"if (j >= r0 - {-early}) {{   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
+                    B.append(f"  const int row = j + {a};")
+                    lines, res = self.scope(grp, a)
+                    B += ["  " + l for l in lines]
+                    for m in grp:
+                        so = self.slot_off(self.depth[m], a)
+                        T = self.T(m)
+                        vt = VEC_TYPE.get((T, V))
+                        if vt:
+                            B.append(f"  *reinterpret_cast<{vt}*>(&ring{m}[{so} + tb]) = make_{vt}({', '.join(res[(m, k)] for k in range(V))});")
+                        else:
+                            for k in range(V):
+                                B.append(f"  ring{m}[{so} + tb + {k}] = {res[(m, k)]};")
+                    B.append("}")
+                if lvl == st.out_level:
+                    B += self.emit_out()
+            bodies.append(B)
 
         # ---- assemble -----------------------------------------------------------------------------
         L: List[str] = []
@@ -476,10 +524,23 @@ class StageEmitter:
             E(f"  {T} acc{v} = {ident};")
         for (d, c), nm in sorted(self.slotvars.items()):
             E(f"  int {nm} = ((((jbeg + {c}) % {d}) + {d}) % {d}) * RW;")
-        E("  for (int j = jbeg; j < r1; ++j) {")
-        L += ["    " + l for l in B]
-        for (d, c), nm in sorted(self.slotvars.items()):
-            E(f"    {nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+        if self.window:
+            byT: Dict[str, List[str]] = {}
+            for n_, T in self.wregs.items():
+                byT.setdefault(T, []).append(n_)
+            for T, ns in byT.items():
+                E(f"  {T} " + ", ".join(f"{n_} = 0" for n_ in sorted(ns)) + ";   // stencil window (rotates by renaming)")
+        nb_ = len(bodies)
+        E(f"  for (int j = jbeg; j < r1; j += {nb_}) {{")
+        for u, B in enumerate(bodies):
+            if nb_ > 1:
+                E(f"    if (j + {u} < r1) {{")
+            L += [("      " if nb_ > 1 else "    ") + l for l in B]
+            # slot offsets are relative to the body's own row, so they advance after every body
+            for (d, c), nm in sorted(self.slotvars.items()):
+                E(("      " if nb_ > 1 else "    ") + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+            if nb_ > 1:
+                E("    }")
         E("  }")
         L += self.emit_reduce_epilogue()
         E("}")

@@ -12,7 +12,8 @@ if wl == "life":
     m.set("cell", life_seed(size[0], 0, size[1]))
 else:
     size = (4096, 4096)
-    m = hydro_machine(size, fmad=(len(sys.argv) > 3 and sys.argv[3] == "fma"))
+    mode = sys.argv[3] if len(sys.argv) > 3 else "exact"
+    m = hydro_machine(size, fmad=(mode == "fma"), fast=(mode == "fast"))
     hydro_set_params(m, size)
     m.call("init")
 for _ in range(steps):
