@@ -363,6 +363,8 @@ class StageEmitter:
             elif op.kind == "Arith":
                 args = [val(a, cur, k) for a in op.args]
                 e = self.arith(op, args)
+                if self.fast and op.ctype == "Double" and op.inst.arg in ("Max", "Min"):
+                    e = f"{'fmax' if op.inst.arg == 'Max' else 'fmin'}({args[0]}, {args[1]})"   # DMNMX instead of DSETP + 2 FSEL
                 if self.fast and op.ctype == "Double" and op.inst.arg in ("Div", "Inv", "Sqrt") and e.count("*") == 0:
                     if op.inst.arg == "Sqrt":
                         e = f"om_fsqrt({args[0]})"
