@@ -151,15 +151,15 @@ __device__ __forceinline__ double om_frsqrt(double x) {
 static inline double om_frcp(double b) { return 1.0 / b; }
 static inline double om_frsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
-__device__ __forceinline__ double om_fdiv_r(double a, double b, double rb) {   // a / b given rb ~ 1/b
-  const double q = a * rb;
-  return fma(fma(-b, q, a), rb, q);
+__device__ __forceinline__ double om_fdiv_r(double a, double b, double rb) {   // a / b given rb = 1/b (<= 1 ulp): <= 1.5 ulp
+  (void)b;
+  return a * rb;
 }
 __device__ __forceinline__ double om_fsqrt(double x) {
-  const double r = om_frsqrt(x);
+  // x * rsqrt(x); the clamp keeps x == 0 -> 0 without a select (0 * rsqrt(tiny) = 0)
+  const double r = om_frsqrt(fmax(x, 1e-300));
   const double s = x * r;
-  const double s2 = fma(fma(-s, s, x), 0.5 * r, s);
-  return x > 0.0 ? s2 : (x == 0.0 ? 0.0 : s);
+  return fma(fma(-s, s, x), 0.5 * r, s);      // one residual correction: <= 1 ulp
 }
 __device__ __forceinline__ float om_frcp(float b) { return 1.0f / b; }
 __device__ __forceinline__ float om_fdiv_r(float a, float b, float rb) { (void)rb; return a / b; }
