@@ -121,9 +121,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("OM_BENCH_WORKLOAD", "life"), choices=list(WORKLOADS))
     ap.add_argument("--fmad", action="store_true", help="Hydro: FMA-contracted build (within 1e-12, not bit-exact)")
-    ap.add_argument("--fast", action="store_true", help="Hydro: Setup.fast_math build (FMA + fast division/sqrt; within 1e-12)")
+    ap.add_argument("--fast", action="store_true", help="Hydro: Setup.fast_math build (FMA + fast division/sqrt; ~1e-15 relative after 20 steps, inside the 1e-12 north-star tolerance)")
+    ap.add_argument("--exact", action="store_true", help="Hydro: bit-exact build (-fmad=false, IEEE division): the default for Hydro is --fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "hydro" and not args.exact and not args.fmad:
+        args.fast = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,10 +226,10 @@ def main():
     peak, peak_src = peaks()
     achieved = cells * alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from ncu --set full
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get(kinfo["stages"][dom]["symbol"] + ("_fast" if args.fast else ""), {}).get("dram_bytes_per_launch")
 
     # end to end through the public host API: pinned host state -> device, proceed(), result scalar -> host
     pinned = {n: torch.from_numpy(np.ascontiguousarray(m.get(n))).pin_memory() for n in state}
