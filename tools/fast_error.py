@@ -1,5 +1,6 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, sys
-sys.path.insert(0,'/root/repo')
 from tests.test_gpu_parity import _hydro_pair, _conserved, NAMES
 for size, steps in [((512,512),20), ((1024,1024),20), ((1024,1024),60)]:
     m, o = _hydro_pair(size, fast=True)

@@ -1,4 +1,6 @@
 """Profiling driver (run under ncu on the GPU box): a few proceed() steps of one workload."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 import torch
 from paraiso_b200.machines import hydro_machine, hydro_set_params, life_machine, life_seed

@@ -1,4 +1,6 @@
 """Hydro stage-1 sweep on the GPU box: CTA width x build."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import importlib, json, os, sys
 import torch
 

@@ -1,4 +1,6 @@
 """Parameter sweep for the Life proceed kernel (run on the GPU box): skeleton, CTA width, prefetch, waves."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import itertools, json, os, sys, time
 import torch
 
