@@ -134,6 +134,7 @@ class Machine:
                 self._fn[k["scalars"]] = f
         self.launches = 0
         self._geom_cache: Dict[str, OmGeom] = {}
+        self._partial: Dict[int, dict] = {}     # static scalar index -> pending all_reduce description
 
     # ---- reference size accessors (PlanTrans.hs:160-215) ------------------------------------
     def om_size(self, k=None):
@@ -204,7 +205,13 @@ class Machine:
             self.launches += 1
             if self.nranks > 1:
                 for r in st["reduces"]:
-                    self._allreduce_slot(r)
+                    if r.get("deferred"):
+                        # nothing on the device consumes this value: each rank keeps its partial result and the
+                        # all_reduce happens when the host reads the scalar (a collective read, see scalar())
+                        for sx in r["stored_to"]:
+                            self._partial[sx] = r
+                    else:
+                        self._allreduce_slot(r)
         if k["scalars"]:
             st0 = k["stages"][0] if k["stages"] else None
             g = self._geom(st0) if st0 else self._geom(dict(symbol="_sc", V=1, w_out=1, smem=0, NT=32, warmup=0))
@@ -310,7 +317,12 @@ class Machine:
         self._fill_ghosts(self.cur[i])
 
     def scalar(self, name: str):
+        """Host read of a static scalar (synchronises).  With several ranks the read of a reduce-derived scalar
+        that no kernel consumes is collective: every rank must call it (the all_reduce was deferred to here)."""
         s = self.statics[self.index[name]]
+        if self.nranks > 1 and self.index[name] in self._partial:
+            r = self._partial.pop(self.index[name])
+            self._allreduce_slot(dict(r, slot=self.index[name]))
         v = self.sc[self.index[name]:self.index[name] + 1].cpu().numpy()
         return v.view(NP_TYPE[s["type"]])[0]
 
