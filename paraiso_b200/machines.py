@@ -23,6 +23,17 @@ def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False,
                          fmad=fmad or fast, verbose=verbose)
 
 
+def build_life_exampled(verbose: bool = False):
+    """examples-old/Life-exampled/LifeMain.hs (Open, 128x128, R-pentomino init): the program whose generated C++
+    the reference ships; used to compare the GPU result with the reference's own output."""
+    return build_machine(life_setup("exampled"), life_om("exampled"), tag="LifeExampled_OO", verbose=verbose)
+
+
+def build_hydro_exampled(verbose: bool = False):
+    """examples-old/Hydro-exampled (Real = Float, Open, 1024x1024)."""
+    return build_machine(hydro_setup(), hydro_om("exampled"), tag="HydroExampled_OO_Float", verbose=verbose)
+
+
 def life_machine(size, device="cuda", **kw) -> Machine:
     desc, so = build_life()
     return Machine(desc, so, size=size, device=device, **kw)
