@@ -31,9 +31,6 @@ from ..native import Setup
 from ..plan import Plan
 from .schedule import KernelSchedule, Op, Stage, schedule_kernel
 
-import os as _os
-
-PF = int(_os.environ.get("OM_PF", "2"))  # cp.async prefetch distance in rows
 
 
 def c_imm(content, ctype: str) -> str:
@@ -122,6 +119,8 @@ class StageEmitter:
         self.ops = ks.ops
         self.V, self.NT = V, NT
         self.fast = bool(getattr(plan.setup, "fast_math", False))
+        self.tuning = plan.setup.tuning
+        self.PF = self.tuning.prefetch_rows     # cp.async prefetch distance in rows
         self.HL, self.HR = _ru(st.halo_x[0], V), _ru(st.halo_x[1], V)
         self.PL, self.PR = _ru(st.pad_x[0], V), _ru(st.pad_x[1], V)
         self.W_OUT = NT * V - self.HL - self.HR
@@ -130,8 +129,8 @@ class StageEmitter:
         self.name = f"om_{om.name}_{ks.name}_stage{stage_idx}"
         self.ring_inputs = [i for i in st.inputs.values() if i.via_smem]
         self.depth: Dict[int, int] = {}
-        for i in self.ring_inputs:        # PF + 1 extra rows for the in-flight async copies
-            self.depth[i.vid] = i.depth + PF + 1
+        for i in self.ring_inputs:        # self.PF + 1 extra rows for the in-flight async copies
+            self.depth[i.vid] = i.depth + self.PF + 1
         for m in st.mats.values():
             self.depth[m.vid] = m.depth
         self.static_of = {i.vid: i.static_idx for i in st.inputs.values()}
@@ -143,13 +142,13 @@ class StageEmitter:
         self.uniform = self._uniform_nodes()
         self.window_u = None
         # row-window mode: MAT-free stages whose inputs are staged in rings keep the stencil window in registers
-        self.window = (not st.mats) and bool(self.ring_inputs) and _os.environ.get("OM_WINDOW", "1") != "0"
+        self.window = (not st.mats) and bool(self.ring_inputs) and self.tuning.row_window
         if self.window:
             self.wcmin = min(i.lag - i.depth + 1 for i in self.ring_inputs)
             self.wcmax = max(i.lag for i in self.ring_inputs)
             self.U = self.wcmax - self.wcmin + 1
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
-        reach = st.warmup + PF + max([abs(i.lag) + i.depth for i in st.inputs.values()] + [0]) + 1
+        reach = st.warmup + self.PF + max([abs(i.lag) + i.depth for i in st.inputs.values()] + [0]) + 1
         assert reach <= APRON_ROWS, f"stage needs {reach} apron rows"
 
     # ------------------------------------------------------------------------------------------
@@ -405,7 +404,7 @@ class StageEmitter:
         mlx, mhx = self.margin_lo[0], self.margin_hi[0]
         warm = st.warmup
         has_ring_in = bool(self.ring_inputs)
-        lead = warm + (PF if has_ring_in else 0)
+        lead = warm + (self.PF if has_ring_in else 0)
 
         # ---- loop body first (it registers slot counters, hoisted values, uniform nodes) -------
         def stage_inputs(B, row_shift: int):
@@ -414,8 +413,8 @@ class StageEmitter:
                 v = i.vid
                 T = self.T(v)
                 nb = TYPE_BYTES[i.ctype] * V
-                so = self.slot_off(self.depth[v], i.lag + PF + row_shift)
-                ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + PF}) * g.pitch + tc;   // advances one row per staged row"
+                so = self.slot_off(self.depth[v], i.lag + self.PF + row_shift)
+                ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + tc;   // advances one row per staged row"
                 if ln not in self.pre:
                     self.pre.append(ln)
                 B.append(f"om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
@@ -425,7 +424,7 @@ class StageEmitter:
                     B.append(f"if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
                 B.append(f"src{v} += g.pitch;")
             B.append("om_cp_async_commit();")
-            B.append(f"om_cp_async_wait<{PF}>();")
+            B.append(f"om_cp_async_wait<{self.PF}>();")
 
         nph = max(len(st.phases), st.out_level)
         bodies: List[List[str]] = []
@@ -495,7 +494,7 @@ class StageEmitter:
         E(f"// stage {self.idx} of kernel `{self.ks.name}` (reduce level {st.level}): "
           f"{len(st.mats)} shared-memory rings for intermediates, {len(self.ring_inputs)} for inputs, "
           f"{nph} phase(s), warm-up {st.warmup} rows, {V} cell(s) per thread")
-        minb = int(_os.environ.get("OM_MINBLOCKS", "0")) if not st.mats else 0
+        minb = self.tuning.min_blocks if not st.mats else 0
         lb = f"__launch_bounds__({NT}, {minb})" if minb else f"__launch_bounds__({NT})"
         E(f"__global__ void {lb} {self.name}_kernel({', '.join(params)}) {{")
         E(f"  constexpr int V = {V}, NT = {NT}, HL = {self.HL}, PL = {self.PL}, RW = {self.RW}, W_OUT = {self.W_OUT};")
@@ -733,7 +732,7 @@ def emit_scalar_stage(om: OM, ks: KernelSchedule) -> Optional[str]:
     return "\n".join(L)
 
 
-def pick_vnt(om: OM, st: Stage, ks: KernelSchedule) -> Tuple[int, int]:
+def pick_vnt(om: OM, st: Stage, ks: KernelSchedule, tuning) -> Tuple[int, int]:
     """Cells per thread and threads per CTA.  16-byte vectors for 4-byte cells; wide double-
     precision DAGs (register-bound) use one cell per thread."""
     sv = om.setup.static_values
@@ -741,5 +740,5 @@ def pick_vnt(om: OM, st: Stage, ks: KernelSchedule) -> Tuple[int, int]:
     types += [ks.ops[v].ctype for (v, _o, _k) in st.reduce_targets]
     width = max([TYPE_BYTES[t] for t in types] + [4])
     if st.mats:
-        return (1, int(_os.environ.get("OM_NT_HEAVY", "256")))
-    return (16 // width if width <= 8 else 1, int(_os.environ.get("OM_NT", "128")))
+        return (1, tuning.threads_heavy)
+    return (16 // width if width <= 8 else 1, tuning.threads_light)

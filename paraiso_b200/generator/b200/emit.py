@@ -65,7 +65,8 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
                                         all(sx not in loaded_scalars for sx in direct_store[slot_to_vid[slot]])),
                               stored_to=direct_store.get(slot_to_vid[slot], []))
                          for (v, rop, slot) in st.reduce_targets],
-                rings=len(em.depth), phases=len(st.phases), warmup=st.warmup))
+                rings=len(em.depth), phases=len(st.phases), warmup=st.warmup,
+                chunk_rows=(0 if (len(st.phases) > 1 or em.smem_bytes() > 48 * 1024) else setup.tuning.chunk_rows_light)))
         kernels.append(dict(
             name=ks.name, stages=stages,
             scalars=(f"om_{om.name}_{ks.name}_scalars" if ks.scalar_stores else None),
@@ -101,9 +102,9 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     emitters = {}
     for ks in schedules:
         for si, st in enumerate(ks.stages):
-            V, NT = (vnt or {}).get((ks.name, si), pick_vnt(om, st, ks))
+            V, NT = (vnt or {}).get((ks.name, si), pick_vnt(om, st, ks, setup.tuning))
             from .warpstream import WarpStreamEmitter, eligible
-            em = (WarpStreamEmitter if eligible(st, V) else StageEmitter)(om, plan, ks, st, si, V, NT)
+            em = (WarpStreamEmitter if eligible(st, V, setup.tuning) else StageEmitter)(om, plan, ks, st, si, V, NT)
             cu.append(em.kernel())
             cu.append(em.launcher())
             cu.append("")

@@ -7,7 +7,7 @@ barriers of cuda.StageEmitter are unnecessary.  Here every warp is independent:
   * a thread owns V consecutive columns and streams along axis 1; the rows of the stencil window
     live in a rotating set of registers (the row loop is unrolled by window + prefetch depth, so the
     rotation is a renaming, not a copy);
-  * each row is read from HBM exactly once per thread with one 128-bit load, issued PREFETCH rows
+  * each row is read from HBM exactly once per thread with one 128-bit load, issued self.PREFETCH rows
     ahead of its use;
   * x-neighbours come from the adjacent lanes with __shfl_up/down; only lane 0 and lane 31 fetch
     their halo cell from global memory (an L1/L2 hit: the neighbouring warp streams that column);
@@ -23,17 +23,13 @@ from typing import Dict, List, Tuple
 from ...om.graph import CPP_TYPE, TYPE_BYTES
 from .cuda import VEC_TYPE, StageEmitter, _m, _ru
 
-import os
-
-PREFETCH = int(os.environ.get("OM_PREFETCH", "2"))  # rows in flight per thread ahead of the stencil window
 
 
-def eligible(st, V: int) -> bool:
+def eligible(st, V: int, tuning) -> bool:
     # Measured on B200 (profiles/r1_life_sweep.txt): for Life the shared-memory ring skeleton with
-    # cp.async staging sustains more bytes in flight per SM (4.9 TB/s) than register streaming
-    # (4.2 TB/s, register-limited occupancy), so streaming is opt-in.
-    mode = os.environ.get("OM_MODE", "ring")
-    if mode != "stream" or st.mats:
+    # cp.async staging sustains more bytes in flight per SM (5.8 TB/s) than register streaming
+    # (4.3 TB/s, register-limited occupancy), so streaming is opt-in (Tuning.skeleton = "stream").
+    if tuning.skeleton != "stream" or st.mats:
         return False
     for i in st.inputs.values():
         if i.rd_xlo > V or i.rd_xhi > V:
@@ -55,7 +51,8 @@ class WarpStreamEmitter(StageEmitter):
         # window of rows (relative to the output row) that the stencil touches, per stage
         self.cmin = min([i.lag - i.depth + 1 for i in ins] + [0])
         self.cmax = max([i.lag for i in ins] + [0])
-        self.U = self.cmax - self.cmin + 1 + PREFETCH
+        self.PREFETCH = self.tuning.stream_prefetch     # rows in flight per thread ahead of the stencil window
+        self.U = self.cmax - self.cmin + 1 + self.PREFETCH
         self.cur_u = 0
 
     def smem_bytes(self) -> int:
@@ -130,7 +127,7 @@ class WarpStreamEmitter(StageEmitter):
         for u in range(U):
             self.cur_u = u
             B: List[str] = [f"if (j + {u} < r1) {{"]
-            B += ["  " + l for l in self.load_row((u + cmax + PREFETCH) % U, f"j + {u + cmax + PREFETCH}")]
+            B += ["  " + l for l in self.load_row((u + cmax + self.PREFETCH) % U, f"j + {u + cmax + self.PREFETCH}")]
             B += ["  " + l for l in self.finish_row((u + cmax) % U)]
             B += ["  " + l for l in self.emit_out(row_expr=f"j + {u}", guard="true")]
             B.append("}")
@@ -138,7 +135,7 @@ class WarpStreamEmitter(StageEmitter):
         L: List[str] = []
         E = L.append
         E(f"// stage {self.idx} of kernel `{self.ks.name}` (reduce level {st.level}): register streaming, no shared memory;")
-        E(f"// stencil rows {cmin}..{cmax}, {PREFETCH} rows prefetched, row loop unrolled x{U}, {V} cell(s) per thread")
+        E(f"// stencil rows {cmin}..{cmax}, {self.PREFETCH} rows prefetched, row loop unrolled x{U}, {V} cell(s) per thread")
         E(f"__global__ void __launch_bounds__({NT}) {self.name}_kernel({', '.join(params)}) {{")
         E(f"  constexpr int V = {V}, NT = {NT}, HL = 0, W_OUT = {self.W_OUT};")
         E("  const int tid = threadIdx.x;")
@@ -169,7 +166,7 @@ class WarpStreamEmitter(StageEmitter):
                 names += [self.hp(i.vid, s, h) for h in range(1, i.rd_xhi + 1)]
             E(f"  {T} " + ", ".join(f"{n} = 0" for n in names) + ";")
         E("  // prologue: fill the stencil window and the prefetch queue of the first row")
-        for c in range(cmin, cmax + PREFETCH):
+        for c in range(cmin, cmax + self.PREFETCH):
             for l in self.load_row(c % U, f"r0 + ({c})"):
                 E("  " + l)
         for c in range(cmin, cmax):

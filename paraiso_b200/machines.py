@@ -11,8 +11,7 @@ from .runtime import Machine
 
 def build_life(fmad: bool = False, verbose: bool = False):
     """examples/Life/Generator.hs (Cyclic, Int): returns (abi, path of libom_Life.so)."""
-    import os
-    return build_machine(life_setup("master"), life_om("master"), tag=os.environ.get("OM_LIFE_TAG", "Life_CC"), fmad=fmad, verbose=verbose)
+    return build_machine(life_setup("master"), life_om("master"), tag="Life_CC", fmad=fmad, verbose=verbose)
 
 
 def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False, fast: bool = False):

@@ -168,19 +168,14 @@ class Machine:
         if occ <= 0:
             raise RuntimeError(f"{st['symbol']}: occupancy query failed ({occ})")
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 4
-        # heavy (shared-memory) stages: one full wave of equally long CTAs; light streaming stages:
-        # a few waves of shorter CTAs so that the tail of the grid does not idle SMs
-        import os
-        heavy = st["phases"] > 1 or st["smem"] > 48 * 1024
-        if heavy:
+        if st.get("chunk_rows", 0) <= 0:
+            # heavy (shared-memory) stages: one full wave of equally long CTAs
             chunks = max(1, min((sms * occ) // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
         else:
-            # measured on B200 (profiles/r1_life_sweep.txt): ~32-row chunks keep the set of concurrently
-            # streamed rows compact and balance the tail; the extra warm-up rows are L2 hits
-            chunks = max(1, nrows // 32)
+            # light streaming stages: short chunks (Tuning.chunk_rows_light, measured in profiles/r1_life_sweep.txt)
+            # keep the set of concurrently streamed rows compact and balance the tail; warm-up rows are L2 hits
+            chunks = max(1, nrows // st["chunk_rows"])
         chunk_rows = -(-nrows // chunks)
-        if os.environ.get("OM_CHUNK_ROWS"):
-            chunk_rows = max(1, int(os.environ["OM_CHUNK_ROWS"]))
         g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
                    cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),

@@ -15,12 +15,15 @@ from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
 
-def _life(size, steps, mode):
-    os.environ["OM_MODE"] = mode
-    try:
-        desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag=f"Life_{mode}")
-    finally:
-        os.environ.pop("OM_MODE")
+def _life(size, steps, mode, window=True):
+    setup = life_setup("master", size=size)
+    setup.tuning.skeleton = mode
+    setup.tuning.row_window = window
+    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}")
+    with open(os.path.join(os.path.dirname(so), "Life_kernels.cu")) as f:
+        src = f.read()
+    assert ("register streaming" in src) == (mode == "stream")
+    assert ("stencil window (rotates by renaming)" in src) == (mode == "ring" and window)
     m = Machine(desc, so, size=size, device="cpu", _emulated=True)
     o = OracleMachine(life_setup("master", size=size), life_om("master"))
     init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
@@ -41,6 +44,11 @@ def test_life_ring_skeleton(size):
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])
 def test_life_register_streaming_skeleton(size):
     _life(size, 4, "stream")
+
+
+@pytest.mark.parametrize("size", [(80, 48), (513, 40)])
+def test_life_ring_skeleton_without_row_window(size):
+    _life(size, 4, "ring", window=False)
 
 
 def test_hydro_master_double_bit_identical():
