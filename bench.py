@@ -25,6 +25,8 @@ WORKLOADS = {
     # name: (per-GPU size, algorithmic bytes per cell update, dtype)
     "life": ((16384, 16384), 8, "i32"),
     "hydro": ((4096, 4096), 64, "f64"),
+    # BASELINE.json configs[3]: one 32768^2 grid slab-decomposed over the GPUs (strong scaling; needs >= 2 GPUs)
+    "hydro32k": ((32768, 32768), 64, "f64"),
 }
 
 
@@ -125,20 +127,23 @@ def main():
     ap.add_argument("--exact", action="store_true", help="Hydro: bit-exact build (-fmad=false, IEEE division): the default for Hydro is --fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload == "hydro" and not args.exact and not args.fmad:
+    if args.workload.startswith("hydro") and not args.exact and not args.fmad:
         args.fast = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size1, alg_bytes, dtype = WORKLOADS[args.workload]
     cfg_name = {"life": "Life 16384x16384 Int32 periodic per GPU (examples/Life/Generator.hs, Cyclic)",
-                "hydro": "Hydro 2D Euler KH 4096x4096 double per GPU (examples/Hydro/HydroMain.hs, Open)"}[args.workload]
+                "hydro": "Hydro 2D Euler KH 4096x4096 double per GPU (examples/Hydro/HydroMain.hs, Open)",
+                "hydro32k": "Hydro 2D Euler KH 32768x32768 double, slab-decomposed over the GPUs (examples/Hydro/HydroMain.hs, Open)"}[args.workload]
+    strong = args.workload == "hydro32k"
 
     if args.impl == "reference":
         if rank != 0:
             return
         # bounded sample: Life 4096x4096 / Hydro 1024x1024 (per-cell cost is size independent once out of cache)
         sample = (4096, 4096) if args.workload == "life" else (1024, 1024)
+        args.workload = "life" if args.workload == "life" else "hydro"
         steps = max(1, min(args.steps, 5 if args.workload == "life" else 3))
         warm = min(args.warmup, 1)
         v, ms = time_cpu(args.workload, sample, steps, warm)
@@ -164,7 +169,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    gsize = (size1[0], size1[1] * world)      # weak scaling: slabs stacked along the outermost axis
+    gsize = size1 if strong else (size1[0], size1[1] * world)      # weak scaling: slabs stacked along the outermost axis
     kw = dict(device=dev, rank=rank, nranks=world)
     if args.workload == "life":
         m = life_machine(gsize, **kw)
@@ -249,7 +254,7 @@ def main():
     line = None
     if rank == 0:
         line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": cfg_name, "global_grid": f"{gsize[0]}x{gsize[1]}", "per_gpu_grid": f"{m.nx}x{m.nyl}",
                            "decomposition": f"slab{world}" if world > 1 else "single", "l2": "state arrays are larger than L2 (no flush needed)",
@@ -263,7 +268,7 @@ def main():
         if not args.no_cpu_baseline:
             sample = (4096, 4096) if args.workload == "life" else (1024, 1024)
             csteps = 5 if args.workload == "life" else 3
-            v, _ = time_cpu(args.workload, sample, csteps, 1)
+            v, _ = time_cpu("life" if args.workload == "life" else "hydro", sample, csteps, 1)
             line["cpu_baseline"] = {"value": v, "unit": "Gcell/s", "cores": cpu_threads(), "kind": "port",
                                     "sample": f"{csteps} proceed() steps of {args.workload} {sample[0]}x{sample[1]}, reference-style C++ (-O3 -fopenmp)"}
         print(json.dumps(line))
