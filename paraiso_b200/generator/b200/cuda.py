@@ -740,5 +740,5 @@ def pick_vnt(om: OM, st: Stage, ks: KernelSchedule, tuning) -> Tuple[int, int]:
     types += [ks.ops[v].ctype for (v, _o, _k) in st.reduce_targets]
     width = max([TYPE_BYTES[t] for t in types] + [4])
     if st.mats:
-        return (1, tuning.threads_heavy)
+        return (tuning.cells_heavy, tuning.threads_heavy)
     return (16 // width if width <= 8 else 1, tuning.threads_light)
