@@ -148,7 +148,9 @@ class StageEmitter:
             self.wcmax = max(i.lag for i in self.ring_inputs)
             self.U = self.wcmax - self.wcmin + 1
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
-        reach = st.warmup + self.PF + max([abs(i.lag) + i.depth for i in st.inputs.values()] + [0]) + 1
+        lags = [i.lag for i in st.inputs.values()] + [0]
+        lows = [i.lag - i.depth + 1 for i in st.inputs.values()] + [0]
+        reach = max(st.warmup + max(0, -min(lows)), max(lags) + self.PF) + 1
         assert reach <= APRON_ROWS, f"stage needs {reach} apron rows"
 
     # ------------------------------------------------------------------------------------------
@@ -522,7 +524,7 @@ class StageEmitter:
         for (v, rop, slot) in st.reduce_targets:
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
-            E(f"  {T} acc{v} = {ident};")
+            E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
         for (d, c), nm in sorted(self.slotvars.items()):
             E(f"  int {nm} = ((((jbeg + {c}) % {d}) + {d}) % {d}) * RW;")
         if self.window:
@@ -640,13 +642,13 @@ class StageEmitter:
             B.append("  }")
         for (v, rop, slot) in st.reduce_targets:
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
-            chain = f"acc{v}"
+            chain = f"acc{slot}"
             for k in range(V):
                 chain = f"{cls}::op({chain}, o{v}_{k})"
-            B.append(f"  if (li_all) {{ acc{v} = {chain}; }}")
+            B.append(f"  if (li_all) {{ acc{slot} = {chain}; }}")
             B.append("  else if (li_any) {")
             for k in range(V):
-                B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{v} = {cls}::op(acc{v}, o{v}_{k});")
+                B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{slot} = {cls}::op(acc{slot}, o{v}_{k});")
             B.append("  }")
         B.append("}")
         return B
@@ -661,9 +663,9 @@ class StageEmitter:
             T = self.T(v)
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
-            L.append(f"  {{ __shared__ {T} red{v}[32]; {T} result;")
+            L.append(f"  {{ __shared__ {T} red{slot}[32]; {T} result;")
             L.append(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y);")
-            L.append(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{v}, {ident}, partials, red_counter + {t}, red{v}, result)) {{")
+            L.append(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{slot}, {ident}, partials, red_counter + {t}, red{slot}, result)) {{")
             L.append(f"      om_slot_store<{T}>(sc, {slot}, result);")
             L.append(f"      red_counter[{t}] = 0u;")
             L.append("    }")

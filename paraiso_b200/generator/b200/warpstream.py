@@ -155,7 +155,7 @@ class WarpStreamEmitter(StageEmitter):
         for (v, rop, slot) in st.reduce_targets:
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
-            E(f"  {T} acc{v} = {ident};")
+            E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
         # register sets
         for i in st.inputs.values():
             T = self.T(i.vid)
