@@ -208,8 +208,7 @@ class Machine:
                     else:
                         self._allreduce_slot(r)
         if k["scalars"]:
-            st0 = k["stages"][0] if k["stages"] else None
-            g = self._geom(st0) if st0 else self._geom(dict(symbol="_sc", V=1, w_out=1, smem=0, NT=32, warmup=0))
+            g = self._geom(k["stages"][0]) if k["stages"] else OmGeom(nx=self.nx, ny=self.ny)   # scalar code only reads nx / ny
             rc = self._fn[k["scalars"]](ctypes.byref(g), self.sc.data_ptr(), stream)
             if rc != 0:
                 raise RuntimeError(f"{k['scalars']} failed with CUDA error {rc}")

@@ -114,3 +114,20 @@ def test_one_dimensional_open_chain_with_cast():
     setup = Setup(local_size=(1500,), boundary=(OPEN,))
     fill = {"t": np.random.default_rng(6).random(mem_shape(setup, om))}
     run_both(om, setup, ["k", "k", "k"], "gen_chain", fill)
+
+
+def test_scalar_only_kernel_and_reduce_of_a_load():
+    a = Named("a", StaticValue(ARRAY, "Int"))
+    n = Named("n", StaticValue(SCALAR, "Int"))
+    tot = Named("tot", StaticValue(SCALAR, "Int"))
+
+    def tick():
+        store(n, load(n) * 2 + 1)
+
+    def total():
+        store(tot, reduce("Sum", load(a)) + load(n))
+    om = lambda: makeOM("Tick", [], [a, n, tot], [("tick", tick), ("total", total)], dim=2)
+    setup = Setup(local_size=(33, 5), boundary=(OPEN, OPEN))
+    fill = {"a": np.random.default_rng(8).integers(0, 9, mem_shape(setup, om)).astype(np.int32)}
+    m, o = run_both(om, setup, ["tick", "tick", "total"], "gen_tick", fill)
+    assert int(m.scalar("n")) == 3 and int(m.scalar("tot")) == int(fill["a"].sum()) + 3

@@ -76,19 +76,22 @@ def _run(which, size, steps, world, port):
     return [ret[r] for r in range(world)]
 
 
-def test_life_two_ranks_equal_one_rank():
+@pytest.mark.parametrize("world", [2, 3])      # 3 ranks: uneven slabs (17 + 17 + 16 rows)
+def test_life_ranks_equal_one_rank(world):
     size, steps = (96, 50), 5
     cell1, pop1 = _run("life", size, steps, 1, 0)
-    parts = _run("life", size, steps, 2, 29611)
+    parts = _run("life", size, steps, world, 29611 + world)
     cell2 = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=0)
+    assert len(parts) == world
     assert np.array_equal(cell1, cell2)
     assert all(p[2] == pop1 for p in parts)      # all_reduce(sum) gives every rank the global population
 
 
-def test_hydro_two_ranks_equal_one_rank():
-    size, steps = (40, 36), 3
+@pytest.mark.parametrize("world", [2, 3])      # 3 ranks: slabs of 13 + 12 + 12 rows, a middle rank without physical margins
+def test_hydro_ranks_equal_one_rank(world):
+    size, steps = (40, 37), 3
     f1, t1 = _run("hydro", size, steps, 1, 0)
-    parts = sorted(_run("hydro", size, steps, 2, 29613), key=lambda p: p[0])
+    parts = sorted(_run("hydro", size, steps, world, 29621 + world), key=lambda p: p[0])
     for n in f1:
         f2 = np.concatenate([p[1][n] for p in parts], axis=0)
         assert np.array_equal(f1[n].view(np.uint64), f2.view(np.uint64)), n
