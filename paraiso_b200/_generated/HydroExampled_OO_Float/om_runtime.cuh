@@ -27,6 +27,8 @@ struct OmGeom {
   int wrap_y_local;              // cyclic axis 1 and this rank holds the whole axis: write ghost rows itself
   int own_r0, own_r1;            // local rows of the reference memory box this rank owns (writes)
   int chunk_rows;                // rows per CTA along axis 1
+  int red_accumulate;            // 1: fold this launch's reduce results into the slots instead of overwriting them
+                                 //    (a stage launched in several row ranges, e.g. boundary rows first, then the interior)
 };
 
 // Scalars (static Scalar-realm variables and reduce results) live in 8-byte device slots.

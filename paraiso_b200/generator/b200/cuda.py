@@ -666,7 +666,7 @@ class StageEmitter:
             L.append(f"  {{ __shared__ {T} red{slot}[32]; {T} result;")
             L.append(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y);")
             L.append(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{slot}, {ident}, partials, red_counter + {t}, red{slot}, result)) {{")
-            L.append(f"      om_slot_store<{T}>(sc, {slot}, result);")
+            L.append(f"      om_slot_store<{T}>(sc, {slot}, g.red_accumulate ? {cls}::op(om_slot_load<{T}>(sc, {slot}), result) : result);")
             L.append(f"      red_counter[{t}] = 0u;")
             L.append("    }")
             L.append("    __syncthreads();")

@@ -39,7 +39,7 @@ class OmGeom(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "nx", "ny", "pitch", "rows", "xorg", "yorg", "y0", "nyl",
         "gx_lo", "gx_hi", "gy_lo", "gy_hi", "cyc_x", "cyc_y", "wrap_y_local",
-        "own_r0", "own_r1", "chunk_rows")]
+        "own_r0", "own_r1", "chunk_rows", "red_accumulate")]
 
 
 def _ru(x, m):
@@ -56,7 +56,7 @@ def slab_rows(ny: int, nranks: int, rank: int):
 
 class Machine:
     def __init__(self, desc: dict, lib_path: str, size=None, device="cuda", rank: int = 0, nranks: int = 1,
-                 group=None, _emulated: bool = False):
+                 group=None, overlap: bool = True, _emulated: bool = False):
         self.desc = desc
         self.name = desc["name"]
         self.device = torch.device(device)
@@ -135,6 +135,9 @@ class Machine:
         self.launches = 0
         self._geom_cache: Dict[str, OmGeom] = {}
         self._partial: Dict[int, dict] = {}     # static scalar index -> pending all_reduce description
+        self.overlap = overlap
+        self._comm_event = None
+        self._comm_stream = torch.cuda.Stream(self.device) if (self.device.type == "cuda" and nranks > 1) else None
 
     # ---- reference size accessors (PlanTrans.hs:160-215) ------------------------------------
     def om_size(self, k=None):
@@ -158,11 +161,14 @@ class Machine:
             return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return ctypes.c_void_p(0)
 
-    def _geom(self, st: dict) -> OmGeom:
-        g = self._geom_cache.get(st["symbol"])
+    def _geom(self, st: dict, rows=None, accumulate: bool = False) -> OmGeom:
+        """Launch geometry of a stage over the rank's owned rows, or over the sub-range `rows` of them."""
+        key = (st["symbol"], rows, accumulate)
+        g = self._geom_cache.get(key)
         if g is not None:
             return g
-        nrows = self.own_r1 - self.own_r0
+        r0, r1 = rows if rows is not None else (self.own_r0, self.own_r1)
+        nrows = r1 - r0
         strips = max(1, -(-(self.cx1 - (self.cx0 // st["V"]) * st["V"]) // st["w_out"]))
         occ = getattr(self.lib, st["symbol"] + "_occupancy")()
         if occ <= 0:
@@ -175,29 +181,68 @@ class Machine:
             # light streaming stages: short chunks (Tuning.chunk_rows_light, measured in profiles/r1_life_sweep.txt)
             # keep the set of concurrently streamed rows compact and balance the tail; warm-up rows are L2 hits
             chunks = max(1, nrows // st["chunk_rows"])
-        chunk_rows = -(-nrows // chunks)
+        chunk_rows = -(-max(nrows, 1) // chunks)
         g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
                    cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),
                    wrap_y_local=int(self.cyc[1] and self.nranks == 1),
-                   own_r0=self.own_r0, own_r1=self.own_r1, chunk_rows=chunk_rows)
-        if strips * (-(-nrows // chunk_rows)) > self.max_blocks:
+                   own_r0=r0, own_r1=r1, chunk_rows=max(1, chunk_rows), red_accumulate=int(accumulate))
+        if strips * (-(-nrows // max(1, chunk_rows))) > self.max_blocks:
             raise ValueError("grid too large for the reduction scratch")
-        self._geom_cache[st["symbol"]] = g
+        self._geom_cache[key] = g
         return g
 
     # ---- kernels ------------------------------------------------------------------------------
+    def _launch(self, st: dict, stream, rows=None, accumulate=False):
+        g = self._geom(st, rows, accumulate)
+        if g.own_r1 <= g.own_r0:
+            return
+        rc = self._fn[st["symbol"]](ctypes.byref(g), self._ptr_cur, self._ptr_alt, self.sc.data_ptr(),
+                                    self.scratch.data_ptr(), stream)
+        if rc != 0:
+            raise RuntimeError(f"{st['symbol']} failed with CUDA error {rc}")
+        self.launches += 1
+
+    def _join_comm(self):
+        """Make the compute stream wait for the ghost-row exchange that is still in flight on the side stream."""
+        if self._comm_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._comm_event)
+            self._comm_event = None
+
     def call(self, kernel: str):
         """Run one OM kernel (`init`, `proceed`, ...) — the emitted member function of that name."""
         k = self.kernels[kernel]
         stream = self._stream()
-        for st in k["stages"]:
-            g = self._geom(st)
-            rc = self._fn[st["symbol"]](ctypes.byref(g), self._ptr_cur, self._ptr_alt, self.sc.data_ptr(),
-                                        self.scratch.data_ptr(), stream)
-            if rc != 0:
-                raise RuntimeError(f"{st['symbol']} failed with CUDA error {rc}")
-            self.launches += 1
+        self._join_comm()
+        stores = k["array_stores"]
+        overlapped = False
+        for si, st in enumerate(k["stages"]):
+            last_storing = self.nranks > 1 and stores and sorted(st["outputs"]) == sorted(stores)
+            # (light streaming stages only: for a heavy stage the two boundary launches pay the full pipeline
+            #  warm-up for a handful of rows, which costs more than the ~20 us exchange they would hide)
+            if (last_storing and self.device.type == "cuda" and self.overlap and st.get("chunk_rows", 0) > 0
+                    and self.nyl >= 4 * max(self.gy_lo, self.gy_hi, 1)):
+                # boundary rows first, then their exchange on a side stream (NCCL send/recv) while the interior
+                # of the slab is computed on the compute stream
+                lo_rows = (self.own_r0, self.yorg + self.gy_hi)                       # rows the lower neighbour needs
+                hi_rows = (self.yorg + self.nyl - self.gy_lo, self.own_r1)           # rows the upper neighbour needs
+                first = True
+                for rng in (lo_rows, hi_rows):
+                    if rng[1] > rng[0]:
+                        self._launch(st, stream, rng, accumulate=not first)
+                        first = False
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self._comm_stream):
+                    self._comm_stream.wait_event(ev)
+                    for s_ in stores:
+                        self._exchange_rows(self.alt[s_])          # alt becomes cur at the swap below
+                    self._comm_event = torch.cuda.Event()
+                    self._comm_event.record(self._comm_stream)
+                self._launch(st, stream, (max(lo_rows[1], lo_rows[0]), hi_rows[0]), accumulate=not first)
+                overlapped = True
+            else:
+                self._launch(st, stream)
             if self.nranks > 1:
                 for r in st["reduces"]:
                     if r.get("deferred"):
@@ -213,11 +258,11 @@ class Machine:
             if rc != 0:
                 raise RuntimeError(f"{k['scalars']} failed with CUDA error {rc}")
             self.launches += 1
-        for s in k["array_stores"]:
+        for s in stores:
             self.cur[s], self.alt[s] = self.alt[s], self.cur[s]
         self._refresh_ptrs()
-        if self.nranks > 1:
-            for s in k["array_stores"]:
+        if self.nranks > 1 and not overlapped:
+            for s in stores:
                 self._exchange_rows(self.cur[s])
 
     def call_stage(self, kernel: str, idx: int):
@@ -294,12 +339,14 @@ class Machine:
         of the reference's memory box that this rank owns; synchronises with the device."""
         i = self.index[name]
         ry, rx = self._box(with_margin)
+        self._join_comm()
         return self.cur[i][ry, rx].contiguous().cpu().numpy()
 
     def set(self, name: str, values: np.ndarray, with_margin: bool = False):
         i = self.index[name]
         ry, rx = self._box(with_margin)
         t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.cur[i].dtype)
+        self._join_comm()
         self.cur[i][ry, rx] = t.to(self.device)
         self._fill_ghosts(self.cur[i])
 
@@ -307,6 +354,7 @@ class Machine:
         """Asynchronous upload of the local interior from a (pinned) host tensor."""
         i = self.index[name]
         ry, rx = self._box(False)
+        self._join_comm()
         self.cur[i][ry, rx].copy_(host, non_blocking=True)
         self._fill_ghosts(self.cur[i])
 
@@ -327,5 +375,6 @@ class Machine:
         self.sc[self.index[name]] = int(z[0])
 
     def synchronize(self):
+        self._join_comm()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
