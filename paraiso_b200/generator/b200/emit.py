@@ -90,7 +90,7 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     schedules: List[KernelSchedule] = []
     slot = nstat
     for k in om.kernels:
-        ks = schedule_kernel(om, k, slot)
+        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold)
         slot += len(ks.reduce_slots)
         schedules.append(ks)
     cu: List[str] = [

@@ -151,8 +151,9 @@ def _pad2(c, dim) -> Cursor:
 
 
 class StageBuilder:
-    def __init__(self, ops: Dict[int, Op], dim: int, stage: Stage):
+    def __init__(self, ops: Dict[int, Op], dim: int, stage: Stage, mat_threshold: int = MAT_THRESHOLD):
         self.ops, self.dim, self.stage = ops, dim, stage
+        self.mat_threshold = mat_threshold
 
     # -- closure of array nodes needed by the stage (through shifts), and scalar roots
     def closure(self, roots: List[int]) -> Set[int]:
@@ -192,7 +193,7 @@ class StageBuilder:
                 cost[v] = 0
                 continue
             c = _cost(op) + sum(cost.get(a, 0) for a in op.args if ops[a].realm == ARRAY)
-            if v in shifted and op.kind not in ("Load", "Imm", "LoadIndex", "Broadcast") and c > MAT_THRESHOLD:
+            if v in shifted and op.kind not in ("Load", "Imm", "LoadIndex", "Broadcast") and c > self.mat_threshold:
                 mats.add(v)
                 c = 0
             cost[v] = c
@@ -309,7 +310,7 @@ class StageBuilder:
         return mat_set
 
 
-def schedule_kernel(om: OM, kernel: Kernel, slot_base: int) -> KernelSchedule:
+def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
@@ -335,7 +336,7 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int) -> KernelSchedule:
         st.reduce_targets = [(ops[v].args[0], ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
                              if rl[ops[v].args[0]] == L]
         roots = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
-        StageBuilder(ops, dim, st).build(list(dict.fromkeys(roots)))
+        StageBuilder(ops, dim, st, mat_threshold).build(list(dict.fromkeys(roots)))
         loaded |= {i.static_idx for i in st.inputs.values()}
         stages.append(st)
     return KernelSchedule(name=kernel.name, ops=ops, stages=stages, scalar_stores=scalar_stores,
