@@ -131,3 +131,17 @@ def test_scalar_only_kernel_and_reduce_of_a_load():
     fill = {"a": np.random.default_rng(8).integers(0, 9, mem_shape(setup, om)).astype(np.int32)}
     m, o = run_both(om, setup, ["tick", "tick", "total"], "gen_tick", fill)
     assert int(m.scalar("n")) == 3 and int(m.scalar("tot")) == int(fill["a"].sum()) + 3
+
+
+def test_initialcondition_example_operators():
+    """examples/InitialCondition: cast, ^ by squaring, ** = exp(log x * y), atan — identical to the oracle when both
+    sides use the same libm (emulated kernels); the CUDA math library is compared with a tolerance in the GPU tests."""
+    from paraiso_b200.examples.initialcondition import initialcondition_om, initialcondition_setup
+    setup = initialcondition_setup((60, 50))
+    desc, so = build_emulated(setup, initialcondition_om(), tag="gen_heart")
+    m = Machine(desc, so, device="cpu", _emulated=True)
+    o = OracleMachine(setup, initialcondition_om())
+    m.call("create"); o.call("create")
+    a, b = m.get("table"), o.array("table")
+    assert np.array_equal(a, b, equal_nan=True)
+    assert np.isfinite(a).sum() > 0.9 * a.size and np.ptp(a[np.isfinite(a)]) > 2.0      # the heart: atan saturates both ways

@@ -87,3 +87,20 @@ def test_hydro_master_float_within_1e5():
     for n in NAMES:
         a, b = m.get(n).astype(np.float64), o.interior(n).astype(np.float64)
         assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 1e-5
+
+
+def test_initialcondition_transcendentals_on_gpu():
+    """examples/InitialCondition (cast, ^, **, atan): CUDA's exp/log/atan against libm, 1e-12."""
+    from oracle.cpu import OracleMachine
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.initialcondition import initialcondition_om, initialcondition_setup
+    from paraiso_b200.runtime import Machine
+    setup = initialcondition_setup()
+    desc, so = build_machine(setup, initialcondition_om(), tag="Heart_OO")
+    m = Machine(desc, so)
+    o = OracleMachine(setup, initialcondition_om())
+    m.call("create"); o.call("create")
+    a, b = m.get("table"), o.array("table")
+    ok = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), ok)
+    assert np.max(np.abs(a[ok] - b[ok])) < 1e-12
