@@ -309,7 +309,7 @@ def hllc(i: int, left: Hydro, right: Hydro) -> Hydro:  # HydroMain.hs:237-276
 
     def selector(a, b, c, d):
         s = select(lt(R(0), shockLeft), a, select(lt(R(0), shockStar), b, select(lt(R(0), shockRight), c, d)))
-        if _Ctx.variant == "master":  # HydroMain.hs:258
+        if _Ctx.variant in ("master", "periodic"):  # HydroMain.hs:258
             return annotate(lambda an: A.add(A.Manifest, an), s)
         return s
     return liftA(selector, left, lesta, rista, right).mapM(bind)
@@ -349,7 +349,9 @@ def buildProceed():  # HydroMain.hs:134-164
     dRG = [bind(load(x)) for x in n["dR"]]
     dR = [bind(broadcast(x)) for x in dRG]
     cell0 = bindPrimitive(dens, velo, pres)
-    cell = boundaryCondition(cell0)
+    # variant "periodic": the same solver without the jet-inflow boundary condition, for Cyclic setups
+    # (analytic tests: advected entropy wave; SURVEY §8 f4, attic/GA.reproduce/massive-test.cu:58-118)
+    cell = cell0 if _Ctx.variant == "periodic" else boundaryCondition(cell0)
     timescale = lambda i: dR[i] / (cell.soundSpeed() + _abs(cell.velocity()[i]))
     dts = bind(foldl1(min_, [timescale(i) for i in range(DIM)]))
     dtG = bind(cflG * reduce("Min", dts))
@@ -369,5 +371,6 @@ def hydro_om(variant: str = "master", real: str = None) -> OM:
     return makeOM("Hydro", [], hydro_vars(), [("init", buildInit), ("proceed", buildProceed)], dim=DIM)
 
 
-def hydro_setup(size=(1024, 1024)) -> Setup:  # HydroMain.hs:290-294
-    return Setup(local_size=tuple(size), boundary=(OPEN, OPEN), directory="./dist/")
+def hydro_setup(size=(1024, 1024), periodic: bool = False) -> Setup:  # HydroMain.hs:290-294
+    from ..annotation import CYCLIC
+    return Setup(local_size=tuple(size), boundary=(CYCLIC, CYCLIC) if periodic else (OPEN, OPEN), directory="./dist/")
