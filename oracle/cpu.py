@@ -12,7 +12,6 @@ import ctypes
 import hashlib
 import os
 import subprocess
-from typing import Dict, Optional
 
 import numpy as np
 

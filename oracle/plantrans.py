@@ -20,7 +20,6 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use th
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Set, Tuple
 
 import numpy as np

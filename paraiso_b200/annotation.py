@@ -8,7 +8,7 @@ frozen dataclass; its Python class plays the role of the Haskell TypeRep.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, FrozenSet, List, Optional, Tuple, Type
+from typing import FrozenSet, Optional, Tuple, Type
 
 
 def empty() -> list:

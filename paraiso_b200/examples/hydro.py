@@ -16,7 +16,7 @@ in the reference; `B` thunks reproduce that (om/builder.py).
 from __future__ import annotations
 
 from fractions import Fraction
-from typing import Callable, List
+from typing import List
 
 from .. import annotation as A
 from ..annotation import OPEN

@@ -25,11 +25,9 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from ... import annotation as A
 from ...om.graph import ARRAY, CPP_TYPE, SCALAR, TYPE_BYTES, OM, imm_value
-from ..native import Setup
 from ..plan import Plan
-from .schedule import KernelSchedule, Op, Stage, schedule_kernel
+from .schedule import KernelSchedule, Op, Stage
 
 
 

@@ -18,10 +18,10 @@ instead of the ~47 of the first shared-memory version (profiles/r1_life_*.txt).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import List
 
-from ...om.graph import CPP_TYPE, TYPE_BYTES
-from .cuda import VEC_TYPE, StageEmitter, _m, _ru
+from ...om.graph import CPP_TYPE
+from .cuda import VEC_TYPE, StageEmitter
 
 
 

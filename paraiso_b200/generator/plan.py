@@ -8,11 +8,11 @@ reference cut literally.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
 from .. import annotation as A
-from ..om.graph import ARRAY, SCALAR, DynValue, Graph, OM
+from ..om.graph import DynValue, OM
 from ..optimization import optimize
 from .native import Setup
 

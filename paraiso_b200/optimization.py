@@ -12,7 +12,7 @@ from __future__ import annotations
 from typing import Dict, List, Set
 
 from . import annotation as A
-from .om.graph import ARRAY, SCALAR, Graph, Kernel, Node, OM
+from .om.graph import SCALAR, Graph, Node, OM
 
 LEVELS = {"Unoptimized": -1, "O0": 0, "O1": 1, "O2": 2, "O3": 3}
 

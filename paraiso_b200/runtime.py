@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from .annotation import CYCLIC, OPEN
+from .annotation import CYCLIC
 
 TORCH_TYPE = {"Int": torch.int32, "Float": torch.float32, "Double": torch.float64, "Bool": torch.bool,
               "Integer": torch.int64}
