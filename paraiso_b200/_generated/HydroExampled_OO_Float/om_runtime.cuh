@@ -69,6 +69,29 @@ __device__ __forceinline__ void om_cp_async_commit() { asm volatile("cp.async.co
 template <int N> __device__ __forceinline__ void om_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// ---- TMA bulk row staging (cp.async.bulk -> UBLKCP) completing on an mbarrier -----------------------------------
+__device__ __forceinline__ void om_mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;\n" ::"r"(count), "r"(a) : "memory");
+}
+__device__ __forceinline__ void om_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void om_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;\n" ::"r"(bytes), "r"(a) : "memory");
+}
+// one contiguous row segment, global -> shared, by the TMA engine; src, dst and bytes are multiples of 16
+__device__ __forceinline__ void om_bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void om_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar), done;
+  do {   // try_wait suspends the thread in hardware up to a time limit; loop until the phase completes
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
 #endif  // OM_EMULATED_INTRINSICS
 
 // ---- reductions (OM/Reduce.hs:9: Max | Min | Sum) ----------------------------------------------

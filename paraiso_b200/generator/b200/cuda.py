@@ -139,6 +139,11 @@ class StageEmitter:
         self.pre: List[str] = []                            # hoisted, before the row loop
         self.uniform = self._uniform_nodes()
         self.window_u = None
+        # TMA bulk staging: one cp.async.bulk per input row issued by thread 0, completion on an mbarrier; needs
+        # 16-byte aligned row segments, i.e. 16-byte vectors per thread
+        self.bulk = (self.tuning.staging == "bulk" and bool(self.ring_inputs) and
+                     all(TYPE_BYTES[i.ctype] * V == 16 for i in self.ring_inputs))
+        self.NBAR = self.PF + 2      # mbarriers in flight: one per staged iteration
         # row-window mode: MAT-free stages whose inputs are staged in rings keep the stencil window in registers
         self.window = (not st.mats) and bool(self.ring_inputs) and self.tuning.row_window
         if self.window:
@@ -159,6 +164,8 @@ class StageEmitter:
         tot = 0
         for v, d in self.depth.items():
             tot = _ru(tot, 16) + d * self.RW * TYPE_BYTES[self.ops[v].ctype]
+        if getattr(self, "bulk", False):
+            tot = _ru(tot, 16) + 8 * self.NBAR
         return _ru(tot, 16)
 
     def _uniform_nodes(self):
@@ -408,6 +415,24 @@ class StageEmitter:
 
         # ---- loop body first (it registers slot counters, hoisted values, uniform nodes) -------
         def stage_inputs(B, row_shift: int):
+            if self.bulk:
+                B.append("// stage the next input rows: one TMA bulk copy (cp.async.bulk / UBLKCP) per row, issued by thread 0,")
+                B.append("// completing on this iteration's mbarrier; the consumer side waits for the barrier armed PF iterations ago")
+                tot = sum(self.RW * TYPE_BYTES[i.ctype] for i in self.ring_inputs)
+                B.append("if (tid == 0) {")
+                B.append(f"  om_mbar_expect_tx(&mbar[bar_i], {tot});")
+                for i in self.ring_inputs:
+                    v = i.vid
+                    T = self.T(v)
+                    so = self.slot_off(self.depth[v], i.lag + self.PF + row_shift)
+                    ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + strip_lo - HL - PL;   // advances one row per staged row"
+                    if ln not in self.pre:
+                        self.pre.append(ln)
+                    B.append(f"  om_bulk_g2s(&ring{v}[{so}], src{v}, {self.RW * TYPE_BYTES[i.ctype]}, &mbar[bar_i]);")
+                    B.append(f"  src{v} += g.pitch;")
+                B.append("}")
+                B.append(f"if (it >= {self.PF}) om_mbar_wait(&mbar[bar_w], bar_wp);")
+                return
             B.append("// stage the next input rows (LDGSTS); the apron rows around every array make bounds checks unnecessary")
             for i in self.ring_inputs:
                 v = i.vid
@@ -506,6 +531,12 @@ class StageEmitter:
             off = _ru(off, 16)
             E(f"  {self.T(v)}* const ring{v} = reinterpret_cast<{self.T(v)}*>(om_smem + {off});  // {d} rows")
             off += d * self.RW * TYPE_BYTES[self.ops[v].ctype]
+        if self.bulk:
+            off = _ru(off, 16)
+            E(f"  uint64_t* const mbar = reinterpret_cast<uint64_t*>(om_smem + {off});   // {self.NBAR} mbarriers")
+            E(f"  if (tid == 0) {{ for (int i = 0; i < {self.NBAR}; ++i) om_mbar_init(&mbar[i], 1); om_mbar_init_fence(); }}")
+            E("  __syncthreads();")
+            E(f"  int it = 0, bar_i = 0, bar_w = {self.NBAR - self.PF}, bar_wp = 1;   // iteration, barrier armed now, barrier awaited now + its parity")
         E(f"  const int cx0 = g.xorg - {mlx}, cx1 = g.xorg + g.nx + {mhx};   // columns of the reference memory box")
         E("  const int cA = (cx0 / V) * V;")
         E("  const int strip_lo = cA + blockIdx.x * W_OUT;            // first output column of this CTA")
@@ -540,6 +571,9 @@ class StageEmitter:
             # slot offsets are relative to the body's own row, so they advance after every body
             for (d, c), nm in sorted(self.slotvars.items()):
                 E(("      " if nb_ > 1 else "    ") + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+            if self.bulk:
+                ind = "      " if nb_ > 1 else "    "
+                E(ind + f"++it; if (++bar_i == {self.NBAR}) bar_i = 0; if (++bar_w == {self.NBAR}) {{ bar_w = 0; bar_wp ^= 1; }}")
             if nb_ > 1:
                 E("    }")
         E("  }")

@@ -15,15 +15,17 @@ from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
 
-def _life(size, steps, mode, window=True):
+def _life(size, steps, mode, window=True, staging="cp_async"):
     setup = life_setup("master", size=size)
     setup.tuning.skeleton = mode
     setup.tuning.row_window = window
-    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}")
+    setup.tuning.staging = staging
+    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}")
     with open(os.path.join(os.path.dirname(so), "Life_kernels.cu")) as f:
         src = f.read()
     assert ("register streaming" in src) == (mode == "stream")
     assert ("stencil window (rotates by renaming)" in src) == (mode == "ring" and window)
+    assert ("om_bulk_g2s" in src) == (staging == "bulk")
     m = Machine(desc, so, size=size, device="cpu", _emulated=True)
     o = OracleMachine(life_setup("master", size=size), life_om("master"))
     init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
@@ -44,6 +46,11 @@ def test_life_ring_skeleton(size):
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])
 def test_life_register_streaming_skeleton(size):
     _life(size, 4, "stream")
+
+
+@pytest.mark.parametrize("size,window", [((80, 48), True), ((513, 40), True), ((1030, 37), False)])
+def test_life_ring_skeleton_with_tma_bulk_staging(size, window):
+    _life(size, 5, "ring", window=window, staging="bulk")
 
 
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])

@@ -29,6 +29,31 @@ def test_life_bit_exact(size, steps):
     assert int(m.scalar("generation")) == steps == int(o.scalar("generation")[0])
 
 
+def test_life_tma_bulk_staging_variant_bit_exact():
+    """Tuning.staging = "bulk": input rows staged by cp.async.bulk (TMA, UBLKCP) completing on mbarriers."""
+    from oracle.cpu import OracleMachine
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.life import life_om, life_setup
+    from paraiso_b200.machines import life_seed
+    from paraiso_b200.runtime import Machine
+    size, steps = (1000, 777), 25
+    setup = life_setup("master")
+    setup.tuning.staging = "bulk"
+    setup.tuning.prefetch_rows = 3
+    desc, so = build_machine(setup, life_om("master"), tag="Life_CC_bulk")
+    with open(so.replace("libom_Life.so", "Life_kernels.cu")) as f:
+        assert "om_bulk_g2s" in f.read()
+    m = Machine(desc, so, size=size)
+    o = OracleMachine(life_setup("master", size=size), life_om("master"), openmp=True, opt="-O3")
+    init = life_seed(size[0], 0, size[1])
+    m.call("init"); o.call("init")
+    m.set("cell", init); o.interior("cell")[...] = init
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    assert np.array_equal(m.get("cell"), o.interior("cell"))
+    assert int(m.scalar("population")) == int(o.scalar("population")[0])
+
+
 def test_life_init_pattern_gosper():
     """examples/Life/main.cpp:21-28 seeds init-pat.txt through the element accessor on the 80x48 default grid."""
     from paraiso_b200.machines import life_machine

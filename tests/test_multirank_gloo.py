@@ -23,7 +23,7 @@ def _worker(rank, world, port, which, size, steps, ret):
     if which == "life":
         from paraiso_b200.examples.life import life_om, life_setup
         from paraiso_b200.machines import life_seed
-        desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring_1")
+        desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring_1_cp_async")
         m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
         m.call("init")
         m.set("cell", life_seed(size[0], m.y0, m.nyl, nx_global=size[0]))
@@ -54,7 +54,7 @@ def _run(which, size, steps, world, port):
         if which == "life":
             from paraiso_b200.examples.life import life_om, life_setup
             from paraiso_b200.machines import life_seed
-            desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring_1")
+            desc, so = build_emulated(life_setup("master", size=size), life_om("master"), tag="Life_ring_1_cp_async")
             m = Machine(desc, so, size=size, device="cpu", _emulated=True)
             m.call("init")
             m.set("cell", life_seed(size[0], 0, size[1]))
