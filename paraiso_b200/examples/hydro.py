@@ -371,6 +371,15 @@ def hydro_om(variant: str = "master", real: str = None) -> OM:
     return makeOM("Hydro", [], hydro_vars(), [("init", buildInit), ("proceed", buildProceed)], dim=DIM)
 
 
-def hydro_setup(size=(1024, 1024), periodic: bool = False) -> Setup:  # HydroMain.hs:290-294
+def hydro_setup(size=(1024, 1024), periodic: bool = False, fast: bool = False) -> Setup:  # HydroMain.hs:290-294
+    """`fast` = Setup.fast_math.  The schedule knobs are the winners of tools/sweep_hydro.py on the B200
+    (profiles/r1_hydro_sweep.txt): the IEEE build is short of registers, so it does without the register prefetch of
+    unstaged inputs; the fast build has the room and is pinned at two CTAs per SM."""
     from ..annotation import CYCLIC
-    return Setup(local_size=tuple(size), boundary=(CYCLIC, CYCLIC) if periodic else (OPEN, OPEN), directory="./dist/")
+    s = Setup(local_size=tuple(size), boundary=(CYCLIC, CYCLIC) if periodic else (OPEN, OPEN), directory="./dist/")
+    s.fast_math = fast
+    if fast:
+        s.tuning.min_blocks_heavy = 2
+    else:
+        s.tuning.direct_prefetch = False
+    return s

@@ -139,6 +139,8 @@ class StageEmitter:
         self.pre: List[str] = []                            # hoisted, before the row loop
         self.uniform = self._uniform_nodes()
         self.window_u = None
+        self.loop_top: List[str] = []                       # first statements of every row iteration
+        self.direct_pf_tags: set = set()
         # TMA bulk staging: one cp.async.bulk per input row issued by thread 0, completion on an mbarrier; needs
         # 16-byte aligned row segments, i.e. 16-byte vectors per thread
         self.bulk = (self.tuning.staging == "bulk" and bool(self.ring_inputs) and
@@ -150,6 +152,8 @@ class StageEmitter:
             self.wcmin = min(i.lag - i.depth + 1 for i in self.ring_inputs)
             self.wcmax = max(i.lag for i in self.ring_inputs)
             self.U = self.wcmax - self.wcmin + 1
+        # inputs read without staging (column offset 0 only) are prefetched one row ahead into registers
+        self.direct_pf = bool(self.tuning.direct_prefetch) and not self.window
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
         lags = [i.lag for i in st.inputs.values()] + [0]
         lows = [i.lag - i.depth + 1 for i in st.inputs.values()] + [0]
@@ -304,6 +308,28 @@ class StageEmitter:
 
         def direct_read(v, cur, k):
             assert cur[0] == 0, "direct global reads are only scheduled for column offset 0"
+            if self.direct_pf:
+                # software pipelining: the row this iteration needs was loaded one iteration ago (loop top), so the
+                # HBM latency overlaps a whole row of arithmetic instead of stalling the few resident warps
+                off = lag + cur[1]
+                tag = f"{v}_{_m(off)}"
+                if tag not in self.direct_pf_tags:
+                    self.direct_pf_tags.add(tag)
+                    T = self.T(v)
+                    sidx = self.static_of[v]
+                    vt = VEC_TYPE.get((T, V))
+                    self.pre.append(f"const {T}* __restrict__ pn{tag} = in{sidx} + (ptrdiff_t)(jbeg + ({off})) * g.pitch + tc;   // next row to prefetch")
+                    if vt:
+                        self.pre.append(f"{vt} nq{tag} = __ldg(reinterpret_cast<const {vt}*>(pn{tag})); pn{tag} += g.pitch;")
+                        self.loop_top.append(f"const {vt} qp{tag} = nq{tag}; nq{tag} = __ldg(reinterpret_cast<const {vt}*>(pn{tag})); pn{tag} += g.pitch;")
+                        for kk in range(V):
+                            self.loop_top.append(f"const {T} dp{tag}_{kk} = qp{tag}.{'xyzw'[kk]};")
+                    else:
+                        for kk in range(V):
+                            self.pre.append(f"{T} nd{tag}_{kk} = __ldg(pn{tag} + {kk});")
+                            self.loop_top.append(f"const {T} dp{tag}_{kk} = nd{tag}_{kk}; nd{tag}_{kk} = __ldg(pn{tag} + g.pitch + {kk});")
+                        self.loop_top.append(f"pn{tag} += g.pitch;")
+                return f"dp{tag}_{k}"
             key = ("direct", v, cur[1])
             if key not in memo:
                 memo[key] = "1"
@@ -370,7 +396,7 @@ class StageEmitter:
                 args = [val(a, cur, k) for a in op.args]
                 e = self.arith(op, args)
                 if self.fast and op.ctype == "Double" and op.inst.arg in ("Max", "Min"):
-                    e = f"{'fmax' if op.inst.arg == 'Max' else 'fmin'}({args[0]}, {args[1]})"   # DMNMX instead of DSETP + 2 FSEL
+                    e = f"{'om_fmax_std' if op.inst.arg == 'Max' else 'om_fmin_std'}({args[0]}, {args[1]})"   # same result, 3 instructions
                 if self.fast and op.ctype == "Double" and op.inst.arg in ("Div", "Inv", "Sqrt") and e.count("*") == 0:
                     if op.inst.arg == "Sqrt":
                         e = f"om_fsqrt({args[0]})"
@@ -511,7 +537,7 @@ class StageEmitter:
                     B.append("}")
                 if lvl == st.out_level:
                     B += self.emit_out()
-            bodies.append(B)
+            bodies.append(self.loop_top + B)
 
         # ---- assemble -----------------------------------------------------------------------------
         L: List[str] = []
@@ -519,7 +545,7 @@ class StageEmitter:
         E(f"// stage {self.idx} of kernel `{self.ks.name}` (reduce level {st.level}): "
           f"{len(st.mats)} shared-memory rings for intermediates, {len(self.ring_inputs)} for inputs, "
           f"{nph} phase(s), warm-up {st.warmup} rows, {V} cell(s) per thread")
-        minb = self.tuning.min_blocks if not st.mats else 0
+        minb = self.tuning.min_blocks if not st.mats else self.tuning.min_blocks_heavy
         lb = f"__launch_bounds__({NT}, {minb})" if minb else f"__launch_bounds__({NT})"
         E(f"__global__ void {lb} {self.name}_kernel({', '.join(params)}) {{")
         E(f"  constexpr int V = {V}, NT = {NT}, HL = {self.HL}, PL = {self.PL}, RW = {self.RW}, W_OUT = {self.W_OUT};")

@@ -100,40 +100,68 @@ class KernelSchedule:
     loaded_arrays: List[int]                      # static idx of arrays read by any stage
 
 
-def fold_ops(g: Graph, dim: int) -> Tuple[Dict[int, Op], List[Tuple[int, int]]]:
+COMMUTATIVE = {"Add", "Mul", "And", "Or", "EQ", "NE"}
+
+
+def fold_ops(g: Graph, dim: int, normalize: bool = True, pull_shifts: bool = False) -> Tuple[Dict[int, Op], List[Tuple[int, int]]]:
     """Fold (inst, value) node pairs into ops and hash-cons them.
 
     The reference never merges structurally identical nodes (an un-`bind`-ed Builder expression
     is re-run at every use, OM/Builder/Internal.hs:163-164, so e.g. Hydro's boundary-condition
     selects exist dozens of times).  All OM instructions are pure, so merging identical
-    (op, operands) pairs, composing chained Shifts and dropping zero Shifts is exact."""
+    (op, operands) pairs, composing chained Shifts and dropping zero Shifts is exact.
+
+    `normalize` orders the operands of commutative IEEE / boolean operators (a + b and b + a are the same bits).
+    `pull_shifts` rewrites f(shift_s a, shift_s b, c) with position-independent c into shift_s f(a, b, c) — the value of
+    a pure per-cell function read at cell x - s — which merges e.g. the "left cell" / "right cell" sound speeds of
+    Hydro's first-order walls (980 -> 936 ops).  It is off: with the present materialisation rule the merged values
+    become 9 more shared-memory rings and a third phase (134 KB, one CTA per SM), a net loss on the B200."""
     ops: Dict[int, Op] = {}
     stores: List[Tuple[int, int]] = []
     canon: Dict[int, int] = {}
     table: Dict[tuple, int] = {}
+    indep: Set[int] = set()          # position-independent values (same for every cell)
+
+    def intern(i: int, inst: Inst, args: List[int], realm, ctype, valid) -> int:
+        payload = inst.arg if inst.op != "Imm" else (repr(inst.arg), inst.imm_type)
+        if normalize and inst.op == "Arith" and inst.arg in COMMUTATIVE and len(args) == 2:
+            args = sorted(args)
+        key = (inst.op, payload, inst.cast_to, tuple(args), realm, ctype)
+        if key in table:
+            return table[key]
+        table[key] = i
+        ops[i] = Op(i, inst.op, inst, list(args), realm, ctype, valid)
+        if realm == SCALAR or inst.op in ("Imm", "Broadcast", "LoadSize") or (inst.op in ("Arith", "Shift") and all(a in indep for a in args)):
+            indep.add(i)
+        return i
+
     for i, nd in enumerate(g.nodes):
         if nd.is_value:
             p, inst = g.pre_inst(i)
             args = [canon[a] for a in g.nodes[p].pre]
+            valid = A.to_maybe(A.Valid, nd.anot)
+            realm, ctype = nd.value.realm, nd.value.type
             if inst.op == "Shift":
                 vec = tuple(inst.arg)
                 src = args[0]
                 if ops[src].kind == "Shift":
                     vec = tuple(a + b for a, b in zip(vec, ops[src].inst.arg))
                     src = ops[src].args[0]
-                if all(x == 0 for x in vec):
+                if all(x == 0 for x in vec) or src in indep:
                     canon[i] = src
                     continue
                 inst = Inst("Shift", vec)
                 args = [src]
-            payload = inst.arg if inst.op != "Imm" else (repr(inst.arg), inst.imm_type)
-            key = (inst.op, payload, inst.cast_to, tuple(args), nd.value.realm, nd.value.type)
-            if key in table:
-                canon[i] = table[key]
-                continue
-            table[key] = i
-            canon[i] = i
-            ops[i] = Op(i, inst.op, inst, args, nd.value.realm, nd.value.type, A.to_maybe(A.Valid, nd.anot))
+            elif pull_shifts and inst.op == "Arith" and realm == ARRAY:
+                vecs = {tuple(ops[a].inst.arg) for a in args if ops[a].kind == "Shift"}
+                if len(vecs) == 1 and all(ops[a].kind == "Shift" or a in indep for a in args):
+                    inner_args = [ops[a].args[0] if ops[a].kind == "Shift" else a for a in args]
+                    # the new per-cell op takes the id of this value's instruction node (unused as an op id, and
+                    # between the operands' ids and i, so ascending ids stay a topological order)
+                    inner = intern(p, inst, inner_args, realm, ctype, None)
+                    inst = Inst("Shift", next(iter(vecs)))
+                    args = [inner]
+            canon[i] = intern(i, inst, args, realm, ctype, valid)
         elif nd.inst.op == "Store":
             stores.append((nd.inst.arg, canon[nd.pre[0]]))
     return ops, stores

@@ -16,8 +16,7 @@ def build_life(fmad: bool = False, verbose: bool = False):
 
 def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False, fast: bool = False):
     """examples/Hydro/HydroMain.hs (Open, Real = Double upstream).  `fast` = Setup.fast_math (implies FMA)."""
-    setup = hydro_setup()
-    setup.fast_math = fast
+    setup = hydro_setup(fast=fast)
     return build_machine(setup, hydro_om("master", real=real), tag=f"Hydro_OO_{real}{'_fast' if fast else ''}",
                          fmad=fmad or fast, verbose=verbose)
 

@@ -77,6 +77,45 @@ def test_hydro_master_double_bit_identical():
     assert m.scalar("time") == o.scalar("time")[0]
 
 
+def _hydro_emulated(size, steps, fast=False, prefetch=None, tag=None):
+    setup = hydro_setup(size, fast=fast)
+    if prefetch is not None:
+        setup.tuning.direct_prefetch = prefetch
+    desc, so = build_emulated(setup, hydro_om("master"), tag=tag)
+    m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+    o = OracleMachine(hydro_setup(size), hydro_om("master"))
+    for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+        m.set_scalar(k, v)
+        o.scalar(k)[0] = v
+    m.call("init"); o.call("init")
+    for t in range(steps):
+        m.call("proceed"); o.call("proceed")
+    return m, o, so
+
+
+def test_hydro_register_prefetch_of_unstaged_inputs_bit_identical():
+    """Tuning.direct_prefetch: inputs read at column offset 0 are loaded one row ahead at the loop top."""
+    m, o, so = _hydro_emulated((70, 37), 2, prefetch=True, tag="Hydro_pf")
+    with open(os.path.join(os.path.dirname(so), "Hydro_kernels.cu")) as f:
+        assert "next row to prefetch" in f.read()
+    for n in ["density", "velocity0", "velocity1", "pressure"]:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
+    assert m.scalar("time") == o.scalar("time")[0]
+
+
+def test_hydro_fast_math_schedule_within_tolerance():
+    """Setup.fast_math: shared reciprocals (a * (1/b)), std::max/min helpers, Goldschmidt sqrt entry points — here with
+    the emulation's exact 1/b and sqrt, so the difference to the reference arithmetic is the re-association only."""
+    m, o, so = _hydro_emulated((64, 48), 3, fast=True, tag="Hydro_fastmath")
+    with open(os.path.join(os.path.dirname(so), "Hydro_kernels.cu")) as f:
+        src = f.read()
+    assert "om_frcp(" in src and "om_fmax_std(" in src and "om_fsqrt(" in src
+    for n in ["density", "velocity0", "velocity1", "pressure"]:
+        a, b = m.get(n), o.interior(n)
+        assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)), n
+    assert abs(m.scalar("time") - o.scalar("time")[0]) <= 1e-12 * o.scalar("time")[0]
+
+
 def test_helloworld_known_answer():
     """examples/HelloWorld: table(x,y) = x*y on 10x20, total = 45*190 = 8550."""
     desc, so = build_emulated(helloworld_setup(), helloworld_om(), tag="Hello")

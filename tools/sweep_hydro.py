@@ -14,9 +14,7 @@ if __name__ == "__main__":
     size = (4096, 4096)
 
     def mk():
-        s = hydro_setup()
-        s.fast_math = fast
-        return s
+        return hydro_setup(fast=fast)
 
     def prepare(m):
         hydro_set_params(m, size)
