@@ -752,8 +752,9 @@ class StageEmitter:
         L.append("  const int nrows = g->own_r1 - g->own_r0;")
         L.append("  if (nrows <= 0 || strips <= 0) return 0;")
         L.append("  const int chunks = (nrows + g->chunk_rows - 1) / g->chunk_rows;")
-        L.append("  static bool attr_set = false;")
-        L.append(f"  if (!attr_set) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; attr_set = true; }}")
+        L.append("  static bool attr_set[64] = {};   // function attributes are per device")
+        L.append("  int dev = 0; cudaGetDevice(&dev);")
+        L.append(f"  if (dev >= 64 || !attr_set[dev]) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; if (dev < 64) attr_set[dev] = true; }}")
         L.append(f"  OM_LAUNCH({self.name}_kernel, dim3(strips, chunks), {self.NT}, {smem}, (cudaStream_t)stream, {', '.join(args)});")
         L.append("  OM_CUDA_CHECK_LAUNCH();")
         L.append("  return 0;")

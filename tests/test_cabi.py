@@ -65,7 +65,7 @@ def test_reference_driver_compiles_and_links_unchanged(name, tag, driver, tmp_pa
     cuda = "/usr/local/cuda"
     exe = str(tmp_path / "main.out")
     cmd = ["/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++", "-std=c++17", "-O1", "-w", f"-I{d}", f"-I{cuda}/include",
-           os.path.join(REF, driver), os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{cuda}/lib64", "-lcudart",
+           os.path.join(REF, driver), os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{cuda}/lib64", "-lcudart", "-lnccl",
            f"-Wl,-rpath,{d}", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]

@@ -20,7 +20,7 @@ def build_driver(name, tag, src):
     exe = os.path.join(out, f"{name.lower()}_driver_{tag}")
     cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-w", f"-I{d}", f"-I{CUDA}/include", os.path.join(ROOT, "tests", "cpp", src),
-           os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{CUDA}/lib64", "-lcudart", f"-Wl,-rpath,{d}", "-o", exe]
+           os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{CUDA}/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{d}", "-o", exe]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -78,3 +78,33 @@ def test_hydro_cpp_class_matches_python_host():
         for v in a.ravel():
             acc += float(v)
         assert float(out[col]) == acc, n
+
+
+def _run(exe, steps, gpus):
+    env = dict(os.environ, OM_B200_GPUS=str(gpus))
+    out = subprocess.run([exe, str(steps)], check=True, capture_output=True, text=True, env=env, timeout=600).stdout
+    return [l for l in out.split("\n") if not l.startswith("NCCL version")]     # (banner printed when NCCL_DEBUG=VERSION)
+
+
+@pytest.mark.parametrize("gpus", [2, 3, 4])
+def test_cpp_classes_on_several_gpus_equal_one_gpu(gpus):
+    """OM_B200_GPUS=N: the same binaries slab-decompose axis 1 over N devices (NCCL ghost-row send/recv, all-reduce of
+    Hydro's dt, deferred all-reduce of Life's population).  Per-cell SSA and min / integer-sum reductions do not
+    depend on the decomposition, so every printed number must be identical to the one-GPU run."""
+    import torch
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    from paraiso_b200.machines import build_hydro, build_life
+    build_life(); build_hydro()
+    life = build_driver("Life", "Life_CC", "life_driver.cpp")
+    hydro = build_driver("Hydro", "Hydro_OO_Double", "hydro_driver.cpp")
+    assert _run(life, 25, gpus) == _run(life, 25, 1)
+    assert _run(hydro, 6, gpus) == _run(hydro, 6, 1)
+
+
+def test_cpp_class_rejects_more_gpus_than_visible():
+    from paraiso_b200.machines import build_life
+    build_life()
+    exe = build_driver("Life", "Life_CC", "life_driver.cpp")
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, env=dict(os.environ, OM_B200_GPUS="64"))
+    assert r.returncode != 0 and "OM_B200_GPUS" in r.stderr
