@@ -65,6 +65,7 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
                               stored_to=direct_store.get(slot_to_vid[slot], []))
                          for (v, rop, slot) in st.reduce_targets],
                 rings=len(em.depth), phases=len(st.phases), warmup=st.warmup,
+                mat_candidates=[dict(c, kernel=ks.name) for c in st.mat_candidates],
                 chunk_rows=(0 if (len(st.phases) > 1 or em.smem_bytes() > 48 * 1024) else setup.tuning.chunk_rows_light)))
         kernels.append(dict(
             name=ks.name, stages=stages,
@@ -89,7 +90,7 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     schedules: List[KernelSchedule] = []
     slot = nstat
     for k in om.kernels:
-        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold)
+        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip)
         slot += len(ks.reduce_slots)
         schedules.append(ks)
     cu: List[str] = [
@@ -136,3 +137,11 @@ def generateIO(setup: Setup, om: OM) -> List[Tuple[str, str]]:  # Generator.hs:2
             f.write(text)
         out.append((path, text))
     return out
+
+
+def describe_only(setup: Setup, om: OM, kernel: str = None) -> List[dict]:
+    """The materialisation genes ({kernel, vid, op, cost, default, chosen}) of a machine, for tuning.local_search."""
+    import json
+    files = dict(generate(setup, om))
+    desc = json.loads(files[f"{om.name}_abi.json"])
+    return [c for k in desc["kernels"] if kernel in (None, k["name"]) for st in k["stages"] for c in st["mat_candidates"]]

@@ -87,6 +87,7 @@ class Stage:
     halo_x: Tuple[int, int] = (0, 0)     # thread coverage beyond the output strip
     pad_x: Tuple[int, int] = (0, 0)      # ring padding beyond thread coverage
     out_level: int = 1                   # phase in which the OUT scope (stores / reduces) runs
+    mat_candidates: List[dict] = field(default_factory=list)   # shifted values: {vid, op, cost, default, chosen}
 
 
 @dataclass
@@ -179,9 +180,11 @@ def _pad2(c, dim) -> Cursor:
 
 
 class StageBuilder:
-    def __init__(self, ops: Dict[int, Op], dim: int, stage: Stage, mat_threshold: int = MAT_THRESHOLD):
+    def __init__(self, ops: Dict[int, Op], dim: int, stage: Stage, mat_threshold: int = MAT_THRESHOLD, mat_flip=()):
         self.ops, self.dim, self.stage = ops, dim, stage
         self.mat_threshold = mat_threshold
+        self.mat_flip = set(mat_flip)          # value ids whose materialise / recompute decision is inverted
+        self.candidates: List[dict] = []       # every shifted value with its cost and decision (for the schedule search)
 
     # -- closure of array nodes needed by the stage (through shifts), and scalar roots
     def closure(self, roots: List[int]) -> Set[int]:
@@ -221,9 +224,13 @@ class StageBuilder:
                 cost[v] = 0
                 continue
             c = _cost(op) + sum(cost.get(a, 0) for a in op.args if ops[a].realm == ARRAY)
-            if v in shifted and op.kind not in ("Load", "Imm", "LoadIndex", "Broadcast") and c > self.mat_threshold:
-                mats.add(v)
-                c = 0
+            if v in shifted and op.kind not in ("Load", "Imm", "LoadIndex", "Broadcast") and c > 0:
+                default = c > self.mat_threshold
+                chosen = default != ((self.stage.kernel, v) in self.mat_flip)
+                self.candidates.append(dict(vid=v, op=op.inst.arg, cost=c, default=default, chosen=chosen))
+                if chosen:
+                    mats.add(v)
+                    c = 0
             cost[v] = c
         return mats
 
@@ -338,7 +345,7 @@ class StageBuilder:
         return mat_set
 
 
-def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD) -> KernelSchedule:
+def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=()) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
@@ -364,7 +371,9 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
         st.reduce_targets = [(ops[v].args[0], ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
                              if rl[ops[v].args[0]] == L]
         roots = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
-        StageBuilder(ops, dim, st, mat_threshold).build(list(dict.fromkeys(roots)))
+        sb = StageBuilder(ops, dim, st, mat_threshold, mat_flip)
+        sb.build(list(dict.fromkeys(roots)))
+        st.mat_candidates = sb.candidates
         loaded |= {i.static_idx for i in st.inputs.values()}
         stages.append(st)
     return KernelSchedule(name=kernel.name, ops=ops, stages=stages, scalar_stores=scalar_stores,

@@ -38,8 +38,9 @@ def _life(size, steps, mode, window=True, staging="cp_async"):
     assert int(m.scalar("generation")) == steps
 
 
-@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37)])
+@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37), (1, 1), (2, 2), (1, 7), (7, 1)])
 def test_life_ring_skeleton(size):
+    """(includes domains narrower than the ghost width: every neighbour of a 1x1 Cyclic grid is the cell itself)"""
     _life(size, 4, "ring")
 
 
@@ -101,6 +102,32 @@ def test_hydro_register_prefetch_of_unstaged_inputs_bit_identical():
     for n in ["density", "velocity0", "velocity1", "pressure"]:
         assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
     assert m.scalar("time") == o.scalar("time")[0]
+
+
+def test_hydro_flipped_materialisation_genes_bit_identical():
+    """Tuning.mat_flip (the per-node Manifest/Delayed genes the schedule search flips): recomputing a value at every
+    cursor instead of keeping it in a shared-memory ring must not change a single bit."""
+    from paraiso_b200.generator.b200.emit import describe_only
+    size = (70, 37)
+    genes = describe_only(hydro_setup(size), hydro_om("master"), "proceed")
+    cheap = sorted([g for g in genes if g["chosen"] and g["cost"] <= 40], key=lambda g: g["vid"])
+    assert len(cheap) >= 3
+    setup = hydro_setup(size)
+    setup.tuning.mat_flip = tuple(("proceed", g["vid"]) for g in cheap[:3])
+    desc, so = build_emulated(setup, hydro_om("master"), tag="Hydro_flip")
+    base_desc, _ = build_emulated(hydro_setup(size), hydro_om("master"))
+    rings = lambda d: [st["rings"] for k in d["kernels"] if k["name"] == "proceed" for st in k["stages"]]
+    assert rings(desc) != rings(base_desc) or desc != base_desc
+    m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+    o = OracleMachine(hydro_setup(size), hydro_om("master"))
+    for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+        m.set_scalar(k, v)
+        o.scalar(k)[0] = v
+    m.call("init"); o.call("init")
+    for t in range(2):
+        m.call("proceed"); o.call("proceed")
+    for n in ["density", "velocity0", "velocity1", "pressure"]:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
 
 
 def test_hydro_fast_math_schedule_within_tolerance():
