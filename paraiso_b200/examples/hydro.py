@@ -380,6 +380,7 @@ def hydro_setup(size=(1024, 1024), periodic: bool = False, fast: bool = False) -
     s.fast_math = fast
     if fast:
         s.tuning.min_blocks_heavy = 2
+        s.tuning.carry_reduces = True     # dt of the next step is reduced in this step's epilogue: +1.4 % (IEEE build: -6 %)
     else:
         s.tuning.direct_prefetch = False
     return s

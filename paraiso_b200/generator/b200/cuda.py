@@ -371,6 +371,9 @@ class StageEmitter:
                 e = ring_read(v, cur, k) if inp.via_smem else direct_read(v, cur, k)
                 memo[key] = e
                 return e
+            if op.kind == "StoredValue":      # carried reduce: the (masked) value this row stores, defined by emit_out
+                memo[key] = f"o{op.args[0]}_{k}"
+                return memo[key]
             if op.kind == "LoadIndex":
                 ax = op.inst.arg
                 nm = f"ix{ax}_{_cur(cur)}_{k}"
@@ -576,7 +579,7 @@ class StageEmitter:
             E("  " + l)
         for l in self.pre:
             E("  " + l)
-        for (v, rop, slot) in st.reduce_targets:
+        for (v, rop, slot) in st.reduce_targets + st.carried:
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
@@ -698,15 +701,25 @@ class StageEmitter:
                 B.append("      }")
             B.append("    } }")
             B.append("  }")
-        for (v, rop, slot) in st.reduce_targets:
+        def accumulate(v, rop, slot, names, ind):
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             chain = f"acc{slot}"
             for k in range(V):
-                chain = f"{cls}::op({chain}, o{v}_{k})"
-            B.append(f"  if (li_all) {{ acc{slot} = {chain}; }}")
-            B.append("  else if (li_any) {")
+                chain = f"{cls}::op({chain}, {names[k]})"
+            B.append(f"{ind}if (li_all) {{ acc{slot} = {chain}; }}")
+            B.append(f"{ind}else if (li_any) {{")
             for k in range(V):
-                B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{slot} = {cls}::op(acc{slot}, o{v}_{k});")
+                B.append(f"{ind}  if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{slot} = {cls}::op(acc{slot}, {names[k]});")
+            B.append(f"{ind}}}")
+        for (v, rop, slot) in st.reduce_targets:
+            accumulate(v, rop, slot, [f"o{v}_{k}" for k in range(V)], "  ")
+        if st.carried:
+            # the level-0 reduce of the NEXT call of this kernel, evaluated on the values just stored (schedule.find_carry)
+            B.append("  {   // carried reduce: next call's level-0 stage becomes an 8-byte copy")
+            lines, res = self.scope([v for (v, _o, _k) in st.carried], 0)
+            B += ["    " + l for l in lines]
+            for (v, rop, slot) in st.carried:
+                accumulate(v, rop, slot, [res[(v, k)] for k in range(V)], "    ")
             B.append("  }")
         B.append("}")
         return B
@@ -714,10 +727,10 @@ class StageEmitter:
     def emit_reduce_epilogue(self) -> List[str]:
         st = self.st
         L: List[str] = []
-        if not st.reduce_targets:
+        if not (st.reduce_targets or st.carried):
             return L
         L.append("  // block reduce -> per-CTA partial -> the last CTA folds all partials (om_runtime.cuh)")
-        for t, (v, rop, slot) in enumerate(st.reduce_targets):
+        for t, (v, rop, slot) in enumerate(st.reduce_targets + st.carried):
             T = self.T(v)
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
@@ -798,7 +811,7 @@ def pick_vnt(om: OM, st: Stage, ks: KernelSchedule, tuning) -> Tuple[int, int]:
     precision DAGs (register-bound) use one cell per thread."""
     sv = om.setup.static_values
     types = [sv[i.static_idx].namee.type for i in st.inputs.values()] + [sv[s].namee.type for (s, _v) in st.store_targets]
-    types += [ks.ops[v].ctype for (v, _o, _k) in st.reduce_targets]
+    types += [ks.ops[v].ctype for (v, _o, _k) in st.reduce_targets + st.carried]
     width = max([TYPE_BYTES[t] for t in types] + [4])
     if st.mats:
         return (tuning.cells_heavy, tuning.threads_heavy)

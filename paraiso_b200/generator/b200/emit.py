@@ -30,7 +30,7 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
     rad_lo, rad_hi = stencil_radius(om)
     pad2 = lambda t: list(t) + [0] * (2 - len(t))
     statics = [dict(name=sv.name, realm=sv.namee.realm, type=sv.namee.type) for sv in om.setup.static_values]
-    nslots = len(statics) + sum(len(ks.reduce_slots) for ks in schedules)
+    nslots = len(statics) + sum(len(ks.reduce_slots) + ks.extra_slots for ks in schedules)
     kernels = []
     # static scalars that some kernel loads: a reduce result stored into any other scalar is only ever read by the
     # host, so with several ranks its all_reduce can wait until the host asks for the value
@@ -63,7 +63,10 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
                               deferred=(slot_to_vid[slot] not in consumed and slot_to_vid[slot] in direct_store and
                                         all(sx not in loaded_scalars for sx in direct_store[slot_to_vid[slot]])),
                               stored_to=direct_store.get(slot_to_vid[slot], []))
-                         for (v, rop, slot) in st.reduce_targets],
+                         for (v, rop, slot) in st.reduce_targets] +
+                        # carried: the next call's level-0 reduce, produced by this stage (consumed on the device)
+                        [dict(op=rop, slot=slot, type=ks.ops[v].ctype, deferred=False, stored_to=[], carried=True)
+                         for (v, rop, slot) in st.carried],
                 rings=len(em.depth), phases=len(st.phases), warmup=st.warmup,
                 mat_candidates=[dict(c, kernel=ks.name) for c in st.mat_candidates],
                 chunk_rows=(0 if (len(st.phases) > 1 or em.smem_bytes() > 48 * 1024) else setup.tuning.chunk_rows_light)))
@@ -72,7 +75,11 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
             scalars=(f"om_{om.name}_{ks.name}_scalars" if ks.scalar_stores else None),
             array_stores=[s for (s, _v) in ks.array_stores],
             scalar_stores=[s for (s, _v) in ks.scalar_stores],
-            loaded_arrays=ks.loaded_arrays))
+            loaded_arrays=ks.loaded_arrays,
+            # carry: {skip_stage, pairs [(reduce slot, carry slot)], arrays, scalars}: when the previous call on this
+            # machine was this kernel and nothing else wrote those statics since, stage `skip_stage` is replaced by
+            # copying each carry slot into its reduce slot
+            carry=ks.carry))
     return dict(
         name=om.name, dim=dim, local_size=(list(setup.local_size) + [1] * (2 - dim)),
         boundary=list(setup.boundary) + [A.OPEN] * (2 - dim),
@@ -90,8 +97,8 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     schedules: List[KernelSchedule] = []
     slot = nstat
     for k in om.kernels:
-        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip)
-        slot += len(ks.reduce_slots)
+        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces)
+        slot += len(ks.reduce_slots) + ks.extra_slots
         schedules.append(ks)
     cu: List[str] = [
         f"// GENERATED by paraiso_b200 (language = B200) for OM `{om.name}` — do not edit.",

@@ -88,6 +88,7 @@ class Stage:
     pad_x: Tuple[int, int] = (0, 0)      # ring padding beyond thread coverage
     out_level: int = 1                   # phase in which the OUT scope (stores / reduces) runs
     mat_candidates: List[dict] = field(default_factory=list)   # shifted values: {vid, op, cost, default, chosen}
+    carried: List[Tuple[int, str, int]] = field(default_factory=list)   # (value id, op, slot): next call's level-0 reduces
 
 
 @dataclass
@@ -99,6 +100,8 @@ class KernelSchedule:
     array_stores: List[Tuple[int, int]]
     reduce_slots: Dict[int, int]                  # Reduce result value id -> slot
     loaded_arrays: List[int]                      # static idx of arrays read by any stage
+    carry: Optional[dict] = None                  # reduce carried to the next call (find_carry)
+    extra_slots: int = 0                          # scalar slots used beyond the reduce slots
 
 
 COMMUTATIVE = {"Add", "Mul", "And", "Or", "EQ", "NE"}
@@ -258,7 +261,7 @@ class StageBuilder:
             if op.kind == "Shift":
                 s = _pad2(op.inst.arg, dim)
                 stack.append((op.args[0], (cur[0] - s[0], cur[1] - s[1]), False))
-            elif op.kind == "Arith":
+            elif op.kind in ("Arith", "StoredValue"):
                 for a in op.args:
                     stack.append((a, cur, False))
         return out
@@ -345,7 +348,99 @@ class StageBuilder:
         return mat_set
 
 
-def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=()) -> KernelSchedule:
+def find_carry(ops: Dict[int, Op], rl: Dict[int, int], reduce_slots: Dict[int, int], array_stores, scalar_stores,
+               levels: List[int]) -> Optional[dict]:
+    """Reduces that can be carried from one call of the kernel to the next.
+
+    Hydro's `proceed` starts with a pass over the four state arrays whose only result is dt = cfl * min(...) — 32 of the
+    96 bytes per cell the step moves.  That reduce reads the arrays at cursor 0 only, and the arrays it
+    reads are exactly the ones the kernel's last stage stores.  So the last stage can evaluate the same expression on
+    the values it is about to store and reduce them for the *next* call; the next call then replaces its level-0 stage
+    by an 8-byte copy, as long as nothing else wrote the arrays or the scalars in between (the host side tracks that).
+
+    Conditions: the level-0 stage stores nothing and each of its reduce arguments (a) contains no Shift, (b) loads only
+    arrays that the kernel stores, all at its last level, (c) loads no scalar the kernel stores and uses no reduce
+    result.  Returns the cloned expression roots (Load s -> StoredValue(value stored to s)) or None."""
+    if len(levels) < 2 or levels[0] != 0:
+        return None
+    if any(rl[v] == 0 for (_s, v) in array_stores):
+        return None
+    level0 = [r for r in sorted(reduce_slots) if rl[ops[r].args[0]] == 0]
+    if not level0:
+        return None
+    last = levels[-1]
+    stored = {s: v for (s, v) in array_stores}
+    if any(rl[v] != last for v in stored.values()):
+        return None
+    scalar_stored = {s for (s, _v) in scalar_stores}
+    clone: Dict[int, int] = {}
+    new_ops: Dict[int, Op] = {}
+    fresh = [max(ops) + 1]
+    arrays: Set[int] = set()
+    scalars: Set[int] = set()
+
+    def scalar_ok(v: int) -> bool:
+        stack, seen = [v], set()
+        while stack:
+            x = stack.pop()
+            if x in seen:
+                continue
+            seen.add(x)
+            o = ops[x]
+            if o.kind == "Reduce":
+                return False
+            if o.kind == "Load":
+                if o.inst.arg in scalar_stored:
+                    return False
+                scalars.add(o.inst.arg)
+            stack.extend(o.args)
+        return True
+
+    def go(v: int) -> Optional[int]:
+        """Clone of v with loads replaced (v itself when nothing below it loads an array); None if not carriable."""
+        if v in clone:
+            return clone[v]
+        o = ops[v]
+        if o.realm == SCALAR:
+            r = v if scalar_ok(v) else None
+        elif o.kind == "Shift":
+            r = None
+        elif o.kind == "Load":
+            if o.inst.arg not in stored:
+                r = None
+            else:
+                arrays.add(o.inst.arg)
+                r = fresh[0]
+                fresh[0] += 1
+                new_ops[r] = Op(r, "StoredValue", Inst("StoredValue", o.inst.arg), [stored[o.inst.arg]], o.realm, o.ctype, None)
+        elif o.kind in ("Imm", "LoadIndex", "LoadSize"):
+            r = v
+        elif o.kind in ("Arith", "Broadcast"):
+            args = [go(a) for a in o.args]
+            if any(a is None for a in args):
+                r = None
+            elif args == o.args:
+                r = v
+            else:
+                r = fresh[0]
+                fresh[0] += 1
+                new_ops[r] = Op(r, o.kind, o.inst, args, o.realm, o.ctype, o.valid)
+        else:
+            r = None
+        clone[v] = r
+        return r
+
+    roots = []
+    for r in level0:
+        c = go(ops[r].args[0])
+        if c is None or c == ops[r].args[0]:
+            return None
+        roots.append((r, c, ops[r].inst.arg))
+    return dict(roots=roots, new_ops=new_ops, arrays=sorted(arrays), scalars=sorted(scalars), level=last)
+
+
+def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=(),
+                    carry_reduces: bool = True) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
@@ -365,16 +460,27 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
                     {rl[ops[v].args[0]] for v in reduce_slots})
     stages: List[Stage] = []
     loaded: Set[int] = set()
+    found = find_carry(ops, rl, reduce_slots, array_stores, scalar_stores, levels) if carry_reduces else None
+    carry = None
+    if found:
+        ops.update(found["new_ops"])
+        nxt = slot_base + len(reduce_slots)
+        carry = dict(skip_stage=0, level=found["level"], arrays=found["arrays"], scalars=found["scalars"],
+                     pairs=[(reduce_slots[r], nxt + n) for n, (r, _c, _o) in enumerate(found["roots"])])
     for L in levels:
         st = Stage(kernel=kernel.name, level=L)
         st.store_targets = [(s, v) for (s, v) in array_stores if rl[v] == L]
         st.reduce_targets = [(ops[v].args[0], ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
                              if rl[ops[v].args[0]] == L]
         roots = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
+        if found and L == found["level"]:
+            st.carried = [(c, rop, carry["pairs"][n][1]) for n, (_r, c, rop) in enumerate(found["roots"])]
+            roots += [c for (c, _o, _k) in st.carried]
         sb = StageBuilder(ops, dim, st, mat_threshold, mat_flip)
         sb.build(list(dict.fromkeys(roots)))
         st.mat_candidates = sb.candidates
         loaded |= {i.static_idx for i in st.inputs.values()}
         stages.append(st)
     return KernelSchedule(name=kernel.name, ops=ops, stages=stages, scalar_stores=scalar_stores,
-                          array_stores=array_stores, reduce_slots=reduce_slots, loaded_arrays=sorted(loaded))
+                          array_stores=array_stores, reduce_slots=reduce_slots, loaded_arrays=sorted(loaded),
+                          carry=carry, extra_slots=len(carry["pairs"]) if carry else 0)

@@ -29,7 +29,7 @@ def eligible(st, V: int, tuning) -> bool:
     # Measured on B200 (profiles/r1_life_sweep.txt): for Life the shared-memory ring skeleton with
     # cp.async staging sustains more bytes in flight per SM (5.8 TB/s) than register streaming
     # (4.3 TB/s, register-limited occupancy), so streaming is opt-in (Tuning.skeleton = "stream").
-    if tuning.skeleton != "stream" or st.mats:
+    if tuning.skeleton != "stream" or st.mats or st.carried:
         return False
     for i in st.inputs.values():
         if i.rd_xlo > V or i.rd_xhi > V:

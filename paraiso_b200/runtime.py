@@ -136,6 +136,7 @@ class Machine:
         self._geom_cache: Dict[str, OmGeom] = {}
         self._partial: Dict[int, dict] = {}     # static scalar index -> pending all_reduce description
         self.overlap = overlap
+        self._carry_kernel: Optional[str] = None   # kernel whose carried reduces are valid for its next call
         self._comm_event = None
         self._comm_stream = torch.cuda.Stream(self.device) if (self.device.type == "cuda" and nranks > 1) else None
 
@@ -216,7 +217,16 @@ class Machine:
         self._join_comm()
         stores = k["array_stores"]
         overlapped = False
+        # carried reduces (schedule.find_carry): the previous call of this same kernel already reduced the arrays it
+        # stored, and nothing has written them (or the scalars involved) since -> the level-0 stage is an 8-byte copy
+        carry = k.get("carry")
+        use_carry = bool(carry) and self._carry_kernel == kernel
+        self._carry_kernel = None
         for si, st in enumerate(k["stages"]):
+            if use_carry and si == carry["skip_stage"]:
+                for (slot, cslot) in carry["pairs"]:
+                    self.sc[slot:slot + 1].copy_(self.sc[cslot:cslot + 1])
+                continue
             last_storing = self.nranks > 1 and stores and sorted(st["outputs"]) == sorted(stores)
             # (light streaming stages only: for a heavy stage the two boundary launches pay the full pipeline
             #  warm-up for a handful of rows, which costs more than the ~20 us exchange they would hide)
@@ -264,6 +274,8 @@ class Machine:
         if self.nranks > 1 and not overlapped:
             for s in stores:
                 self._exchange_rows(self.cur[s])
+        if carry:
+            self._carry_kernel = kernel
 
     def call_stage(self, kernel: str, idx: int):
         """Launch a single array stage without the pointer swap (benchmark / profiling hook)."""
@@ -347,6 +359,7 @@ class Machine:
         ry, rx = self._box(with_margin)
         t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.cur[i].dtype)
         self._join_comm()
+        self._carry_kernel = None
         self.cur[i][ry, rx] = t.to(self.device)
         self._fill_ghosts(self.cur[i])
 
@@ -355,6 +368,7 @@ class Machine:
         i = self.index[name]
         ry, rx = self._box(False)
         self._join_comm()
+        self._carry_kernel = None
         self.cur[i][ry, rx].copy_(host, non_blocking=True)
         self._fill_ghosts(self.cur[i])
 
@@ -372,6 +386,7 @@ class Machine:
         s = self.statics[self.index[name]]
         z = np.zeros(1, dtype=np.int64)
         z.view(NP_TYPE[s["type"]])[0] = value
+        self._carry_kernel = None
         self.sc[self.index[name]] = int(z[0])
 
     def synchronize(self):

@@ -130,6 +130,41 @@ def test_hydro_flipped_materialisation_genes_bit_identical():
         assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
 
 
+def test_hydro_carried_dt_reduce_bit_identical_and_invalidated_by_host_writes():
+    """Tuning.carry_reduces: the last stage of `proceed` also reduces dt for the next call, which then replaces its
+    level-0 stage by a slot copy.  A host write to an array or a scalar in between must bring the stage back."""
+    size = (70, 37)
+    setup = hydro_setup(size)
+    setup.tuning.carry_reduces = True
+    desc, so = build_emulated(setup, hydro_om("master"), tag="Hydro_carry")
+    k = [k for k in desc["kernels"] if k["name"] == "proceed"][0]
+    assert k["carry"] and k["carry"]["skip_stage"] == 0 and k["carry"]["arrays"] == [7, 8, 9, 10]
+    m = Machine(desc, so, size=size, device="cpu", _emulated=True)
+    o = OracleMachine(hydro_setup(size), hydro_om("master"))
+    for kk, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+        m.set_scalar(kk, v)
+        o.scalar(kk)[0] = v
+    m.call("init"); o.call("init")
+    names = ["density", "velocity0", "velocity1", "pressure"]
+    launches = []
+    for t in range(6):
+        if t == 3:      # host write to an array: the carried dt is stale
+            a = m.get("pressure", with_margin=True)
+            a[20:25, 30:40] *= 4.0
+            m.set("pressure", a, with_margin=True)
+            o.array("pressure")[20:25, 30:40] *= 4.0
+        if t == 5:      # host write to a scalar the reduce depends on
+            m.set_scalar("dR0", 0.5 / size[0])
+            o.scalar("dR0")[0] = 0.5 / size[0]
+        before = m.launches
+        m.call("proceed"); o.call("proceed")
+        launches.append(m.launches - before)
+        for n in names:
+            assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), (t, n)
+        assert m.scalar("time") == o.scalar("time")[0], t
+    assert launches == [3, 2, 2, 3, 2, 3]     # dt stage + flux stage + scalar kernel, or without the dt stage
+
+
 def test_hydro_fast_math_schedule_within_tolerance():
     """Setup.fast_math: shared reciprocals (a * (1/b)), std::max/min helpers, Goldschmidt sqrt entry points — here with
     the emulation's exact 1/b and sqrt, so the difference to the reference arithmetic is the re-association only."""

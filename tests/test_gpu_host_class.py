@@ -13,14 +13,15 @@ GEN = os.path.join(ROOT, "paraiso_b200", "_generated")
 CUDA = "/usr/local/cuda"
 
 
-def build_driver(name, tag, src):
+def build_driver(name, tag, src, lib=None):
     d = os.path.join(GEN, tag)
+    lib = lib or f"om_{name}"
     out = os.path.join(ROOT, "tests", "cpp", "_build")
     os.makedirs(out, exist_ok=True)
     exe = os.path.join(out, f"{name.lower()}_driver_{tag}")
     cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-w", f"-I{d}", f"-I{CUDA}/include", os.path.join(ROOT, "tests", "cpp", src),
-           os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{CUDA}/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{d}", "-o", exe]
+           os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-l{lib}", f"-L{CUDA}/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{d}", "-o", exe]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -58,14 +59,16 @@ def test_life_cpp_class_matches_oracle():
     assert out[1] == f"population {pop}"
 
 
-def test_hydro_cpp_class_matches_python_host():
+@pytest.mark.parametrize("fast", [False, True])     # fast: carried dt reduce + per-node schedule genes in both hosts
+def test_hydro_cpp_class_matches_python_host(fast):
     from paraiso_b200.machines import build_hydro, hydro_machine, hydro_set_params
-    build_hydro()
+    build_hydro(fast=fast)
     steps = 5
-    exe = build_driver("Hydro", "Hydro_OO_Double", "hydro_driver.cpp")
+    exe = build_driver("Hydro", "Hydro_OO_Double_fast" if fast else "Hydro_OO_Double", "hydro_driver.cpp",
+                       lib="om_Hydro_fma" if fast else None)
     out = subprocess.run([exe, str(steps)], check=True, capture_output=True, text=True).stdout.split()
     W, H = int(out[0]), int(out[1])
-    m = hydro_machine((W, H))
+    m = hydro_machine((W, H), fast=fast)
     hydro_set_params(m, (W, H))
     m.call("init")
     for _ in range(steps):
@@ -100,6 +103,9 @@ def test_cpp_classes_on_several_gpus_equal_one_gpu(gpus):
     hydro = build_driver("Hydro", "Hydro_OO_Double", "hydro_driver.cpp")
     assert _run(life, 25, gpus) == _run(life, 25, 1)
     assert _run(hydro, 6, gpus) == _run(hydro, 6, 1)
+    build_hydro(fast=True)
+    hydro_fast = build_driver("Hydro", "Hydro_OO_Double_fast", "hydro_driver.cpp", lib="om_Hydro_fma")
+    assert _run(hydro_fast, 6, gpus) == _run(hydro_fast, 6, 1)
 
 
 def test_cpp_class_rejects_more_gpus_than_visible():

@@ -33,7 +33,9 @@ def _worker(rank, world, port, which, size, steps, ret):
     else:
         from paraiso_b200.examples.hydro import hydro_om, hydro_setup
         from paraiso_b200.machines import hydro_set_params
-        desc, so = build_emulated(hydro_setup(size), hydro_om("master"))
+        setup = hydro_setup(size)
+        setup.tuning.carry_reduces = which == "hydro_carry"
+        desc, so = build_emulated(setup, hydro_om("master"), tag="Hydro_carry" if which == "hydro_carry" else None)
         m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
         hydro_set_params(m, size)
         m.call("init")
@@ -63,7 +65,9 @@ def _run(which, size, steps, world, port):
             return m.get("cell"), int(m.scalar("population"))
         from paraiso_b200.examples.hydro import hydro_om, hydro_setup
         from paraiso_b200.machines import hydro_set_params
-        desc, so = build_emulated(hydro_setup(size), hydro_om("master"))
+        setup = hydro_setup(size)
+        setup.tuning.carry_reduces = which == "hydro_carry"
+        desc, so = build_emulated(setup, hydro_om("master"), tag="Hydro_carry" if which == "hydro_carry" else None)
         m = Machine(desc, so, size=size, device="cpu", _emulated=True)
         hydro_set_params(m, size)
         m.call("init")
@@ -96,3 +100,14 @@ def test_hydro_ranks_equal_one_rank(world):
         f2 = np.concatenate([p[1][n] for p in parts], axis=0)
         assert np.array_equal(f1[n].view(np.uint64), f2.view(np.uint64)), n
     assert all(p[2] == t1 for p in parts)        # all_reduce(min) of the CFL time step
+
+
+def test_hydro_carried_dt_reduce_two_ranks():
+    """Tuning.carry_reduces with several ranks: the carried dt is all_reduced right after the stage that produced it."""
+    size, steps = (40, 37), 4
+    f1, t1 = _run("hydro", size, steps, 1, 0)
+    parts = sorted(_run("hydro_carry", size, steps, 2, 29641), key=lambda p: p[0])
+    for n in f1:
+        f2 = np.concatenate([p[1][n] for p in parts], axis=0)
+        assert np.array_equal(f1[n].view(np.uint64), f2.view(np.uint64)), n
+    assert all(p[2] == t1 for p in parts)
