@@ -678,7 +678,13 @@ class StageEmitter:
             P(f"{T}* __restrict__ po{s} = out{s} + (ptrdiff_t)r0 * g.pitch + tc;   // advances one row per output row")
             B.append(f"  {{ {T}* __restrict__ p = po{s}; po{s} += g.pitch;")
             if vt:
-                B.append(f"    if (li_all) {{ *reinterpret_cast<{vt}*>(p) = make_{vt}({', '.join(f'o{v}_{k}' for k in range(V))}); }}")
+                mk = f"make_{vt}({', '.join(f'o{v}_{k}' for k in range(V))})"
+                if self.tuning.store_hint == "cs":      # streaming store (evict-first): the row is not read again before the next step
+                    B.append(f"    if (li_all) {{ __stcs(reinterpret_cast<{vt}*>(p), {mk}); }}")
+                elif self.tuning.store_hint == "cg":
+                    B.append(f"    if (li_all) {{ __stcg(reinterpret_cast<{vt}*>(p), {mk}); }}")
+                else:
+                    B.append(f"    if (li_all) {{ *reinterpret_cast<{vt}*>(p) = {mk}; }}")
                 B.append("    else if (li_any) {")
                 for k in range(V):
                     B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = o{v}_{k};")

@@ -38,6 +38,8 @@ static const cudaError_t cudaSuccess = 0;
 static const int cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
 template <class F> static cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 template <class F> static cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 
