@@ -34,6 +34,10 @@
  * On Cyclic axes the ghost cells of an array must be valid before a stage reads it; stages keep them valid
  * for the arrays they write (x always; y when wrap_y_local), the host refreshes them after host writes and,
  * with several ranks, exchanges the y ghost rows.
+ * Rank-3 machines (ABI version 2) stack `nz + gz_lo + gz_hi` planes of `rows * pitch` elements along axis 2
+ * (`plane` = that stride, interior plane 0 at device plane `zorg`; the aprons surround the whole stack); a launch
+ * covers device planes [own_z0, own_z1) with one layer of CTAs per plane, and the host copies the ghost planes of a
+ * Cyclic axis 2 after each store.  Rank-1 / rank-2 callers pass nz = 1, plane = 0, own_z0 = 0, own_z1 = 1.
  */
 #pragma once
 #include "om_Life_abi.h"

@@ -132,8 +132,11 @@ class StageEmitter:
         for m in st.mats.values():
             self.depth[m.vid] = m.depth
         self.static_of = {i.vid: i.static_idx for i in st.inputs.values()}
-        self.margin_lo = tuple(plan.lower_margin) + (0,) * (2 - len(plan.lower_margin))
-        self.margin_hi = tuple(plan.upper_margin) + (0,) * (2 - len(plan.upper_margin))
+        self.margin_lo = tuple(plan.lower_margin) + (0,) * (3 - len(plan.lower_margin))
+        self.margin_hi = tuple(plan.upper_margin) + (0,) * (3 - len(plan.upper_margin))
+        self.dim3 = plan.setup.dim == 3                    # rank 3: one plane of axis 2 per blockIdx.z (schedule.lower_z)
+        self.zoff_of = {i.vid: i.zoff for i in st.inputs.values()}
+        self.zdefs: Dict[str, str] = {}                     # plane-shifted base pointers, defined at the kernel top
         self.slotvars: Dict[Tuple[int, int], str] = {}     # (depth, row offset c) -> element-offset variable
         self.uniform_used: Dict[int, None] = {}
         self.pre: List[str] = []                            # hoisted, before the row loop
@@ -163,6 +166,22 @@ class StageEmitter:
     # ------------------------------------------------------------------------------------------
     def T(self, v) -> str:
         return CPP_TYPE[self.ops[v].ctype]
+
+    def inp(self, v: int) -> str:
+        """Base pointer of the static array behind Load value v — for rank 3, of the plane that virtual input reads."""
+        sidx = self.static_of[v]
+        if not self.dim3:
+            return f"in{sidx}"
+        nm = f"inz{v}"
+        self.zdefs[nm] = f"const {self.T(v)}* __restrict__ {nm} = in{sidx} + (ptrdiff_t)(zp + ({self.zoff_of[v]})) * g.plane;"
+        return nm
+
+    def outp(self, s: int, T: str) -> str:
+        if not self.dim3:
+            return f"out{s}"
+        nm = f"outz{s}"
+        self.zdefs[nm] = f"{T}* __restrict__ {nm} = out{s} + (ptrdiff_t)zp * g.plane;"
+        return nm
 
     def smem_bytes(self) -> int:
         tot = 0
@@ -221,7 +240,7 @@ class StageEmitter:
             elif op.kind == "Imm":
                 out.append(f"const {T} s{v} = {c_imm(op.inst.arg, op.ctype)};")
             elif op.kind == "LoadSize":
-                out.append(f"const {T} s{v} = ({T}){'g.nx' if op.inst.arg == 0 else 'g.ny'};")
+                out.append(f"const {T} s{v} = ({T}){('g.nx', 'g.ny', 'g.nz')[op.inst.arg]};")
             elif op.kind == "Arith":
                 out.append(f"const {T} s{v} = {self.arith(op, ['s%d' % a for a in op.args])};")
             else:
@@ -318,7 +337,7 @@ class StageEmitter:
                     T = self.T(v)
                     sidx = self.static_of[v]
                     vt = VEC_TYPE.get((T, V))
-                    self.pre.append(f"const {T}* __restrict__ pn{tag} = in{sidx} + (ptrdiff_t)(jbeg + ({off})) * g.pitch + tc;   // next row to prefetch")
+                    self.pre.append(f"const {T}* __restrict__ pn{tag} = {self.inp(v)} + (ptrdiff_t)(jbeg + ({off})) * g.pitch + tc;   // next row to prefetch")
                     if vt:
                         self.pre.append(f"{vt} nq{tag} = __ldg(reinterpret_cast<const {vt}*>(pn{tag})); pn{tag} += g.pitch;")
                         self.loop_top.append(f"const {vt} qp{tag} = nq{tag}; nq{tag} = __ldg(reinterpret_cast<const {vt}*>(pn{tag})); pn{tag} += g.pitch;")
@@ -339,7 +358,7 @@ class StageEmitter:
                 tag = f"{v}_{_m(cy)}"
                 vt = VEC_TYPE.get((T, V))
                 # no bounds predicates: the ABI requires OM_APRON_ROWS allocated rows around every array
-                lines.append(f"const {T}* __restrict__ pd{tag} = in{sidx} + (ptrdiff_t)(row + ({cy})) * g.pitch + tc;")
+                lines.append(f"const {T}* __restrict__ pd{tag} = {self.inp(v)} + (ptrdiff_t)(row + ({cy})) * g.pitch + tc;")
                 if vt:
                     lines.append(f"const {vt} qd{tag} = __ldg(reinterpret_cast<const {vt}*>(pd{tag}));")
                     for kk in range(V):
@@ -376,7 +395,7 @@ class StageEmitter:
                 return memo[key]
             if op.kind == "LoadIndex":
                 ax = op.inst.arg
-                nm = f"ix{ax}_{_cur(cur)}_{k}"
+                nm = f"ix{ax}_{_cur(cur)}_{k}" + (f"_z{_m(op.zoff)}" if ax == 2 else "")
                 if (nm, "def") not in memo:
                     memo[(nm, "def")] = "1"
                     if ax == 0:
@@ -385,11 +404,13 @@ class StageEmitter:
                             self.pre_names.add(hn)
                             self.pre.append(f"const int {hn} = g.cyc_x ? om_wrap(tc + {k} + ({cur[0]}) - g.xorg, g.nx) : (tc + {k} + ({cur[0]}) - g.xorg);")
                         lines.append(f"const int {nm} = {hn};")
-                    else:
+                    elif ax == 1:
                         lines.append(f"const int {nm} = g.cyc_y ? om_wrap(row + ({cur[1]}) - g.yorg + g.y0, g.ny) : (row + ({cur[1]}) - g.yorg + g.y0);")
+                    else:      # axis 2: the CTA's plane plus the offset lower_z gave this node
+                        lines.append(f"const int {nm} = g.cyc_z ? om_wrap(zp + ({op.zoff}) - g.zorg, g.nz) : (zp + ({op.zoff}) - g.zorg);")
                 e = f"(({T}){nm})"
             elif op.kind == "LoadSize":
-                e = f"(({T}){'g.nx' if op.inst.arg == 0 else 'g.ny'})"
+                e = f"(({T}){('g.nx', 'g.ny', 'g.nz')[op.inst.arg]})"
             elif op.kind == "Shift":
                 s = tuple(op.inst.arg) + (0,) * (2 - len(op.inst.arg))
                 e = val(op.args[0], (cur[0] - s[0], cur[1] - s[1]), k)
@@ -454,7 +475,7 @@ class StageEmitter:
                     v = i.vid
                     T = self.T(v)
                     so = self.slot_off(self.depth[v], i.lag + self.PF + row_shift)
-                    ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + strip_lo - HL - PL;   // advances one row per staged row"
+                    ln = f"const {T}* __restrict__ src{v} = {self.inp(v)} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + strip_lo - HL - PL;   // advances one row per staged row"
                     if ln not in self.pre:
                         self.pre.append(ln)
                     B.append(f"  om_bulk_g2s(&ring{v}[{so}], src{v}, {self.RW * TYPE_BYTES[i.ctype]}, &mbar[bar_i]);")
@@ -468,7 +489,7 @@ class StageEmitter:
                 T = self.T(v)
                 nb = TYPE_BYTES[i.ctype] * V
                 so = self.slot_off(self.depth[v], i.lag + self.PF + row_shift)
-                ln = f"const {T}* __restrict__ src{v} = in{i.static_idx} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + tc;   // advances one row per staged row"
+                ln = f"const {T}* __restrict__ src{v} = {self.inp(v)} + (ptrdiff_t)(jbeg + {i.lag + self.PF}) * g.pitch + tc;   // advances one row per staged row"
                 if ln not in self.pre:
                     self.pre.append(ln)
                 B.append(f"om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
@@ -573,6 +594,10 @@ class StageEmitter:
         E("  const int r0 = g.own_r0 + blockIdx.y * g.chunk_rows;")
         E("  const int r1 = min(r0 + g.chunk_rows, g.own_r1);")
         E(f"  const int jbeg = r0 - {lead};")
+        if self.dim3:
+            E("  const int zp = g.own_z0 + blockIdx.z;                 // this CTA's plane of axis 2 (device plane index)")
+            for l in self.zdefs.values():
+                E("  " + l)
         for l in self.scalar_code(list(dict.fromkeys(st.scalar_roots))):
             E("  " + l)
         for l in self.uniform_code():
@@ -629,6 +654,14 @@ class StageEmitter:
         hi = tuple(hi) + (0,) * (2 - len(hi))
         return lo[0], hi[0], lo[1], hi[1]
 
+    def valid_box_z(self, v) -> Tuple[int, int]:
+        """(lb_z, ub_z) of the node's Valid region along axis 2 (rank-3 machines)."""
+        from ..plan import _valid_to_lower, _valid_to_upper
+        if not self.dim3:
+            return 0, 0
+        valid = self.ops[v].valid
+        return _valid_to_lower(self.plan.setup, valid)[2], _valid_to_upper(self.plan.setup, valid)[2]
+
     def emit_out(self, row_expr: str = "j", guard: str = "j >= r0") -> List[str]:
         """Stores + reduce accumulation for one output row.  The common case (all V lanes of the thread
         inside the strip's output range, no ghost cell to mirror) is a single predicated vector store;
@@ -659,6 +692,10 @@ class StageEmitter:
             if lby or uby:
                 need_gmy = True
                 conds_row.append(f"(gmy >= {lby}) && (gmy < memy - {uby})")
+            lbz, ubz = self.valid_box_z(v)
+            if lbz or ubz:
+                P(f"const int gmz = zp - g.zorg + {self.margin_lo[2]}, memz = g.nz + {self.margin_lo[2] + self.margin_hi[2]};   // plane in the reference memory box")
+                conds_row.append(f"(gmz >= {lbz}) && (gmz < memz - {ubz})")
             for k in range(V):
                 conds = list(conds_row)
                 if lbx or ubx:
@@ -675,7 +712,7 @@ class StageEmitter:
         for (s, v) in st.store_targets:
             T = self.T(v)
             vt = VEC_TYPE.get((T, V))
-            P(f"{T}* __restrict__ po{s} = out{s} + (ptrdiff_t)r0 * g.pitch + tc;   // advances one row per output row")
+            P(f"{T}* __restrict__ po{s} = {self.outp(s, T)} + (ptrdiff_t)r0 * g.pitch + tc;   // advances one row per output row")
             B.append(f"  {{ {T}* __restrict__ p = po{s}; po{s} += g.pitch;")
             if vt:
                 mk = f"make_{vt}({', '.join(f'o{v}_{k}' for k in range(V))})"
@@ -741,7 +778,7 @@ class StageEmitter:
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             L.append(f"  {{ __shared__ {T} red{slot}[32]; {T} result;")
-            L.append(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y);")
+            L.append(f"    {T}* partials = reinterpret_cast<{T}*>(red_partials + (size_t){t} * gridDim.x * gridDim.y * gridDim.z);")
             L.append(f"    if (om_block_reduce_finalize<{cls}, {T}, NT>(acc{slot}, {ident}, partials, red_counter + {t}, red{slot}, result)) {{")
             L.append(f"      om_slot_store<{T}>(sc, {slot}, g.red_accumulate ? {cls}::op(om_slot_load<{T}>(sc, {slot}), result) : result);")
             L.append(f"      red_counter[{t}] = 0u;")
@@ -774,7 +811,9 @@ class StageEmitter:
         L.append("  static bool attr_set[64] = {};   // function attributes are per device")
         L.append("  int dev = 0; cudaGetDevice(&dev);")
         L.append(f"  if (dev >= 64 || !attr_set[dev]) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; if (dev < 64) attr_set[dev] = true; }}")
-        L.append(f"  OM_LAUNCH({self.name}_kernel, dim3(strips, chunks), {self.NT}, {smem}, (cudaStream_t)stream, {', '.join(args)});")
+        L.append("  const int planes = g->own_z1 - g->own_z0;   // rank 3: one layer of CTAs per plane of axis 2 (1 otherwise)")
+        L.append("  if (planes <= 0) return 0;")
+        L.append(f"  OM_LAUNCH({self.name}_kernel, dim3(strips, chunks, planes), {self.NT}, {smem}, (cudaStream_t)stream, {', '.join(args)});")
         L.append("  OM_CUDA_CHECK_LAUNCH();")
         L.append("  return 0;")
         L.append("}")

@@ -89,8 +89,8 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
 
 
 def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] = None) -> List[Tuple[str, str]]:
-    if setup.dim > 2:
-        raise NotImplementedError("the B200 backend emits 1-D and 2-D machines (SURVEY §8 f3 lists rank 3 as next)")
+    if setup.dim > 3:
+        raise NotImplementedError("the B200 backend emits rank-1, rank-2 and rank-3 machines")
     plan = om_translate(setup, om0)
     om = plan.om
     nstat = len(om.setup.static_values)
@@ -121,17 +121,15 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
             cu.append(sc)
             cu.append("")
     desc = describe(om, plan, schedules, emitters)
-    cu.append(f'extern "C" int om_{om.name}_abi_version(void) {{ return 1; }}')
+    cu.append(f'extern "C" int om_{om.name}_abi_version(void) {{ return 2; }}')
     with open(os.path.join(CSRC, "om_runtime.cuh")) as f:
         runtime = f.read()
     files = [(f"{om.name}_kernels.cu", "\n".join(cu) + "\n"),
              (f"{om.name}_abi.json", json.dumps(desc, indent=1) + "\n"),
              ("om_runtime.cuh", runtime)]
-    try:
-        from .host import emit_host
-        files += emit_host(desc)
-    except ImportError:
-        pass
+    from .host import emit_abi_header, emit_host
+    # (the C++ host class is emitted for rank 1 and 2; rank-3 machines are driven through the C ABI, e.g. runtime.Machine)
+    files += emit_host(desc) if setup.dim <= 2 else [(f"{om.name}_abi.h", emit_abi_header(desc))]
     return files
 
 

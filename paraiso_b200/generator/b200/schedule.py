@@ -42,6 +42,7 @@ class Op:
     realm: str
     ctype: str
     valid: Optional[A.Valid] = None
+    zoff: int = 0              # rank-3 machines after lower_z: axis-2 offset of a Load / LoadIndex(2) relative to the CTA's plane
 
 
 @dataclass
@@ -70,6 +71,7 @@ class InputArr:
     early: int = 0
     rd_xlo: int = 0
     rd_xhi: int = 0
+    zoff: int = 0         # rank 3: the plane this virtual input reads, relative to the CTA's plane
 
 
 @dataclass
@@ -169,6 +171,77 @@ def fold_ops(g: Graph, dim: int, normalize: bool = True, pull_shifts: bool = Fal
         elif nd.inst.op == "Store":
             stores.append((nd.inst.arg, canon[nd.pre[0]]))
     return ops, stores
+
+
+def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int, Op], List[Tuple[int, int]]]:
+    """Rank-3 machines: turn the op DAG into a rank-2 DAG per plane of axis 2.
+
+    A CTA of a rank-3 machine works inside one plane z of axis 2 (blockIdx.z), streaming along axis 1 exactly like a
+    rank-2 kernel.  The axis-2 component of every Shift is pushed down to the leaves: the value of v needed at plane
+    offset cz is a copy of v's expression whose array Loads (and LoadIndex 2) carry `zoff = cz` — a "virtual input"
+    that is simply the same static array addressed one or more planes away — and whose Shifts keep their (axis 0,
+    axis 1) part only.  This is the reference's own evaluation rule (every Delayed value is recomputed at the cursor
+    it is requested at, PlanTrans.hs:527-544) applied to axis 2; along axes 0 and 1 the shared-memory rings of the
+    rank-2 schedule still remove the recomputation.  Neighbouring planes are re-read by the CTAs of the planes next to
+    them, i.e. from L2."""
+    def zc(a: int, cz: int) -> int:      # position-independent values exist once
+        o = ops[a]
+        if o.realm == SCALAR or o.kind in ("Imm", "Broadcast", "LoadSize") or (o.kind == "LoadIndex" and o.inst.arg != 2):
+            return 0
+        return cz
+    need: Dict[int, Set[int]] = {v: set() for v in ops}
+    for (_s, v) in stores:
+        need[v].add(0)
+    for v in sorted(ops):
+        if ops[v].kind == "Reduce":
+            need[v].add(0)
+    for v in sorted(ops, reverse=True):
+        o = ops[v]
+        for cz in need[v]:
+            if o.kind == "Shift":
+                a = o.args[0]
+                need[a].add(zc(a, cz - tuple(o.inst.arg)[2]))
+            elif o.kind in ("Reduce", "Broadcast") or o.realm == SCALAR:
+                for a in o.args:
+                    need[a].add(0)
+            else:
+                for a in o.args:
+                    need[a].add(zc(a, cz))
+    out: Dict[int, Op] = {}
+    m: Dict[Tuple[int, int], int] = {}
+    table: Dict[tuple, int] = {}
+    for v in sorted(ops):
+        o = ops[v]
+        for cz in sorted(need[v]):
+            inst, kind, zoff = o.inst, o.kind, 0
+            if kind == "Shift":
+                vec = tuple(o.inst.arg)
+                a = o.args[0]
+                src = m[(a, zc(a, cz - vec[2]))]
+                if vec[0] == 0 and vec[1] == 0:
+                    m[(v, cz)] = src
+                    continue
+                if out[src].kind == "Shift":     # compose with a Shift that survived below
+                    vec = (vec[0] + out[src].inst.arg[0], vec[1] + out[src].inst.arg[1], 0)
+                    src = out[src].args[0]
+                    if vec[0] == 0 and vec[1] == 0:
+                        m[(v, cz)] = src
+                        continue
+                inst, args = Inst("Shift", (vec[0], vec[1])), [src]
+            elif kind in ("Reduce", "Broadcast") or o.realm == SCALAR:
+                args = [m[(a, 0)] for a in o.args]
+            else:
+                args = [m[(a, zc(a, cz))] for a in o.args]
+                if kind == "Load" or (kind == "LoadIndex" and o.inst.arg == 2):
+                    zoff = cz
+            payload = inst.arg if inst.op != "Imm" else (repr(inst.arg), inst.imm_type)
+            key = (inst.op, payload, inst.cast_to, tuple(args), o.realm, o.ctype, zoff)
+            if key not in table:
+                nid = len(out)
+                out[nid] = Op(nid, kind, inst, args, o.realm, o.ctype, o.valid, zoff)
+                table[key] = nid
+            m[(v, cz)] = table[key]
+    return out, [(s_, m[(v, 0)]) for (s_, v) in stores]
 
 
 def _cost(op: Op) -> int:
@@ -337,7 +410,7 @@ class StageBuilder:
                 via = any(c[0] != 0 for (_n, c) in d["uses"])
                 st.inputs[b] = InputArr(static_idx=op.inst.arg, vid=b, ctype=op.ctype, lag=lag[b], depth=d["depth"],
                                         via_smem=via, xlo=xlo[b], xhi=xhi[b], early=early[b],
-                                        rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"])
+                                        rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"], zoff=op.zoff)
         nlev = max([m.level for m in st.mats.values()] + [st.out_level])
         st.phases = [[m.vid for m in sorted(st.mats.values(), key=lambda m: m.vid) if m.level == l] for l in range(1, nlev + 1)]
         st.warmup = -min([0] + [m.early for m in st.mats.values()] + [i.early for i in st.inputs.values() if i.via_smem])
@@ -444,6 +517,8 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
+    if dim == 3:
+        ops, stores = lower_z(ops, stores)
     # reduce levels
     rl: Dict[int, int] = {}
     for v in sorted(ops):

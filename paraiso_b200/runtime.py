@@ -39,7 +39,8 @@ class OmGeom(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "nx", "ny", "pitch", "rows", "xorg", "yorg", "y0", "nyl",
         "gx_lo", "gx_hi", "gy_lo", "gy_hi", "cyc_x", "cyc_y", "wrap_y_local",
-        "own_r0", "own_r1", "chunk_rows", "red_accumulate")]
+        "own_r0", "own_r1", "chunk_rows", "red_accumulate",
+        "nz", "plane", "zorg", "gz_lo", "gz_hi", "cyc_z", "own_z0", "own_z1")]
 
 
 def _ru(x, m):
@@ -64,17 +65,23 @@ class Machine:
             raise RuntimeError("paraiso_b200 machines run on CUDA devices only (no CPU fallback)")
         self.emulated = _emulated
         self.lib = ctypes.CDLL(lib_path)   # raises OSError if the extension is missing
-        if getattr(self.lib, f"om_{self.name}_abi_version")() != 1:
+        if getattr(self.lib, f"om_{self.name}_abi_version")() != 2:
             raise RuntimeError("ABI version mismatch")
         self.rank, self.nranks, self.group = rank, nranks, group
         size = list(size) if size is not None else list(desc["local_size"])
-        size = size + [1] * (2 - len(size))
-        self.nx, self.ny = int(size[0]), int(size[1])
-        self.boundary = desc["boundary"]
-        self.mlo, self.mhi = desc["lower_margin"], desc["upper_margin"]
-        rlo, rhi = desc["radius_lo"], desc["radius_hi"]
+        size = size + [1] * (3 - len(size))
+        self.nx, self.ny, self.nz = int(size[0]), int(size[1]), int(size[2])
+        self.dim3 = desc["dim"] == 3
+        if not self.dim3 and self.nz != 1:
+            raise ValueError("a rank-2 machine takes a (nx, ny) size")
+        if self.dim3 and nranks > 1:
+            raise NotImplementedError("rank-3 machines run on one GPU (the slab decomposition splits axis 1 of rank-2 machines)")
+        pad3 = lambda t, fill: list(t) + [fill] * (3 - len(t))
+        self.boundary = pad3(desc["boundary"], "Open")
+        self.mlo, self.mhi = pad3(desc["lower_margin"], 0), pad3(desc["upper_margin"], 0)
+        rlo, rhi = pad3(desc["radius_lo"], 0), pad3(desc["radius_hi"], 0)
         self.cyc = [b == CYCLIC for b in self.boundary]
-        for ax in range(2):
+        for ax in range(3):
             if not self.cyc[ax]:
                 assert self.mlo[ax] == rlo[ax] and self.mhi[ax] == rhi[ax], "Open margins must equal the stencil radius"
         self.y0, self.nyl = slab_rows(self.ny, nranks, rank)
@@ -92,6 +99,11 @@ class Machine:
             self.own_r0 = 0 if first else self.yorg
             self.own_r1 = self.rows if last else self.yorg + self.nyl
         self.cx0, self.cx1 = self.xorg - self.mlo[0], self.xorg + self.nx + self.mhi[0]
+        # rank 3: planes of rows * pitch elements stacked along axis 2 (ghost planes included); rank 2: one plane
+        self.gz_lo, self.gz_hi = rlo[2], rhi[2]
+        self.zorg = self.gz_lo
+        self.planes = self.nz + self.gz_lo + self.gz_hi
+        self.own_z0, self.own_z1 = (self.zorg, self.zorg + self.nz) if self.cyc[2] else (0, self.planes)
         # storage
         self.statics = desc["statics"]
         self.index = {s["name"]: i for i, s in enumerate(self.statics)}
@@ -104,15 +116,15 @@ class Machine:
                 # APRON rows of zero-initialised slack above and below: the kernels read a few rows
                 # beyond the slab while filling their pipelines and do not bounds-check (C-ABI contract)
                 for lst in (self.cur, self.alt):
-                    full = torch.zeros((self.rows + 2 * APRON, self.pitch), dtype=t, device=self.device)
+                    full = torch.zeros((self.planes * self.rows + 2 * APRON, self.pitch), dtype=t, device=self.device)
                     self._storage.append(full)
-                    lst.append(full[APRON:APRON + self.rows])
+                    lst.append(full[APRON:APRON + self.planes * self.rows])
             else:
                 self.cur.append(None)
                 self.alt.append(None)
         self.nslots = desc["nslots"]
         self.sc = torch.zeros(self.nslots, dtype=torch.int64, device=self.device)
-        self.max_blocks = 1 << 16
+        self.max_blocks = 1 << (18 if self.dim3 else 16)
         nred = max([len(st["reduces"]) for k in desc["kernels"] for st in k["stages"]] + [1])
         self.scratch = torch.zeros(256 + 8 * self.max_blocks * nred, dtype=torch.uint8, device=self.device)
         self.kernels = {k["name"]: k for k in desc["kernels"]}
@@ -142,11 +154,11 @@ class Machine:
 
     # ---- reference size accessors (PlanTrans.hs:160-215) ------------------------------------
     def om_size(self, k=None):
-        return self.nx * self.ny if k is None else (self.nx, self.ny)[k]
+        return self.nx * self.ny * self.nz if k is None else (self.nx, self.ny, self.nz)[k]
 
     def om_memory_size(self, k=None):
-        m = (self.nx + self.mlo[0] + self.mhi[0], self.ny + self.mlo[1] + self.mhi[1])
-        return m[0] * m[1] if k is None else m[k]
+        m = (self.nx + self.mlo[0] + self.mhi[0], self.ny + self.mlo[1] + self.mhi[1], self.nz + self.mlo[2] + self.mhi[2])
+        return m[0] * m[1] * m[2] if k is None else m[k]
 
     def om_lower_margin(self, k): return self.mlo[k]
     def om_upper_margin(self, k): return self.mhi[k]
@@ -187,8 +199,10 @@ class Machine:
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
                    cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),
                    wrap_y_local=int(self.cyc[1] and self.nranks == 1),
-                   own_r0=r0, own_r1=r1, chunk_rows=max(1, chunk_rows), red_accumulate=int(accumulate))
-        if strips * (-(-nrows // max(1, chunk_rows))) > self.max_blocks:
+                   own_r0=r0, own_r1=r1, chunk_rows=max(1, chunk_rows), red_accumulate=int(accumulate),
+                   nz=self.nz, plane=(self.rows * self.pitch if self.dim3 else 0), zorg=self.zorg, gz_lo=self.gz_lo,
+                   gz_hi=self.gz_hi, cyc_z=int(self.cyc[2]), own_z0=self.own_z0, own_z1=self.own_z1)
+        if strips * (-(-nrows // max(1, chunk_rows))) * (self.own_z1 - self.own_z0) > self.max_blocks:
             raise ValueError("grid too large for the reduction scratch")
         self._geom_cache[key] = g
         return g
@@ -263,13 +277,15 @@ class Machine:
                     else:
                         self._allreduce_slot(r)
         if k["scalars"]:
-            g = self._geom(k["stages"][0]) if k["stages"] else OmGeom(nx=self.nx, ny=self.ny)   # scalar code only reads nx / ny
+            g = self._geom(k["stages"][0]) if k["stages"] else OmGeom(nx=self.nx, ny=self.ny, nz=self.nz)   # scalar code only reads the sizes
             rc = self._fn[k["scalars"]](ctypes.byref(g), self.sc.data_ptr(), stream)
             if rc != 0:
                 raise RuntimeError(f"{k['scalars']} failed with CUDA error {rc}")
             self.launches += 1
         for s in stores:
             self.cur[s], self.alt[s] = self.alt[s], self.cur[s]
+            if self.dim3 and self.cyc[2]:
+                self._fill_z_ghosts(self.cur[s])     # whole planes (their x / y ghost cells were written by the kernel)
         self._refresh_ptrs()
         if self.nranks > 1 and not overlapped:
             for s in stores:
@@ -323,8 +339,38 @@ class Machine:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
+    def _v3(self, a: torch.Tensor) -> torch.Tensor:
+        """[plane, row, column] view of an array (one plane for rank-2 machines)."""
+        return a.view(self.planes, self.rows, self.pitch)
+
+    def _fill_z_ghosts(self, a: torch.Tensor):
+        """Rank 3, Cyclic axis 2: ghost planes <- the interior planes they wrap to (contiguous device copies)."""
+        a3 = self._v3(a)
+        z0, z1 = self.zorg, self.zorg + self.nz
+        if self.gz_lo:
+            a3[0:self.gz_lo] = a3[z1 - self.gz_lo:z1]
+        if self.gz_hi:
+            a3[z1:z1 + self.gz_hi] = a3[z0:z0 + self.gz_hi]
+
     def _fill_ghosts(self, a: torch.Tensor):
         """Host-initiated ghost refresh after the host wrote an array (not on the step path)."""
+        if self.dim3:
+            a3 = self._v3(a)
+            x0, x1 = self.xorg, self.xorg + self.nx
+            y0, y1 = self.yorg, self.yorg + self.nyl
+            if self.cyc[0]:
+                if self.gx_lo:
+                    a3[:, :, x0 - self.gx_lo:x0] = a3[:, :, x1 - self.gx_lo:x1]
+                if self.gx_hi:
+                    a3[:, :, x1:x1 + self.gx_hi] = a3[:, :, x0:x0 + self.gx_hi]
+            if self.cyc[1]:
+                if self.gy_lo:
+                    a3[:, 0:self.gy_lo] = a3[:, y1 - self.gy_lo:y1]
+                if self.gy_hi:
+                    a3[:, y1:y1 + self.gy_hi] = a3[:, y0:y0 + self.gy_hi]
+            if self.cyc[2]:
+                self._fill_z_ghosts(a)
+            return
         x0, x1 = self.xorg, self.xorg + self.nx
         if self.cyc[0]:
             if self.gx_lo:
@@ -342,34 +388,39 @@ class Machine:
 
     # ---- host accessors (PlanTrans.hs:117-157) ------------------------------------------------------
     def _box(self, with_margin: bool):
+        """(plane, row, column) slices of the interior, or of the part of the reference's memory box this rank owns."""
         if with_margin:
-            return slice(self.own_r0, self.own_r1), slice(self.cx0, self.cx1)
-        return slice(self.yorg, self.yorg + self.nyl), slice(self.xorg, self.xorg + self.nx)
+            return slice(self.own_z0, self.own_z1), slice(self.own_r0, self.own_r1), slice(self.cx0, self.cx1)
+        return (slice(self.zorg, self.zorg + self.nz), slice(self.yorg, self.yorg + self.nyl),
+                slice(self.xorg, self.xorg + self.nx))
 
     def get(self, name: str, with_margin: bool = False) -> np.ndarray:
         """Local slab of a static Array as [i1, i0] (axis 0 fastest), optionally with the margins
         of the reference's memory box that this rank owns; synchronises with the device."""
         i = self.index[name]
-        ry, rx = self._box(with_margin)
+        rz, ry, rx = self._box(with_margin)
         self._join_comm()
-        return self.cur[i][ry, rx].contiguous().cpu().numpy()
+        out = self._v3(self.cur[i])[rz, ry, rx].contiguous().cpu().numpy()
+        return out if self.dim3 else out[0]
 
     def set(self, name: str, values: np.ndarray, with_margin: bool = False):
         i = self.index[name]
-        ry, rx = self._box(with_margin)
+        rz, ry, rx = self._box(with_margin)
         t = torch.as_tensor(np.ascontiguousarray(values), dtype=self.cur[i].dtype)
         self._join_comm()
         self._carry_kernel = None
-        self.cur[i][ry, rx] = t.to(self.device)
+        dst = self._v3(self.cur[i])[rz, ry, rx]
+        dst[...] = t.to(self.device).reshape(dst.shape)
         self._fill_ghosts(self.cur[i])
 
     def set_from_host(self, name: str, host: torch.Tensor):
         """Asynchronous upload of the local interior from a (pinned) host tensor."""
         i = self.index[name]
-        ry, rx = self._box(False)
+        rz, ry, rx = self._box(False)
         self._join_comm()
         self._carry_kernel = None
-        self.cur[i][ry, rx].copy_(host, non_blocking=True)
+        dst = self._v3(self.cur[i])[rz, ry, rx]
+        dst.copy_(host.view(dst.shape), non_blocking=True)
         self._fill_ghosts(self.cur[i])
 
     def scalar(self, name: str):

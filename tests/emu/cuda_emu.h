@@ -122,10 +122,11 @@ static void om_emu_launch(K kernel, dim3 grid, unsigned nt, size_t smem, Args...
   std::vector<std::thread> ths;
   for (unsigned t = 0; t < nt; ++t) {
     ths.emplace_back([=]() {
+      for (unsigned bz = 0; bz < grid.z; ++bz)
       for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
           threadIdx = {t, 0, 0};
-          blockIdx = {bx, by, 0};
+          blockIdx = {bx, by, bz};
           kernel(args...);
           emu_block->bar->arrive_and_wait();   // CTAs run one after another
         }

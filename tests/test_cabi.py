@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(name):
         pytest.skip(f"cannot load {LIBS[name]}: {e}")
     for s in syms:
         assert hasattr(lib, s), s
-    assert getattr(lib, f"om_{name}_abi_version")() == 1
+    assert getattr(lib, f"om_{name}_abi_version")() == 2
 
 
 def test_header_is_plain_c():

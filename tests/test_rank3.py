@@ -1,0 +1,99 @@
+"""Rank-3 machines: the axis-2 part of every shift is lowered to plane-shifted virtual inputs
+(schedule.lower_z), one layer of CTAs per plane.  Emulated kernels against the oracle, which is rank-generic like the
+reference's PlanTrans."""
+import numpy as np
+import pytest
+
+from oracle.cpu import OracleMachine
+from paraiso_b200.annotation import CYCLIC, OPEN
+from paraiso_b200.generator.native import Setup
+from paraiso_b200.om.builder import (StaticValue, bind, broadcast, cast, imm, load, loadIndex, loadSize, makeOM, reduce, select, shift,
+                                     store, eq, ge, le, sqrt, sum_)
+from paraiso_b200.om.graph import ARRAY, SCALAR, Named
+from paraiso_b200.runtime import Machine
+from tests.emu.build_emu import build_emulated
+
+
+def mem_shape3(setup, om_fn):
+    from paraiso_b200.generator.plan import translate
+    p = translate(setup, om_fn())
+    return tuple(reversed(p.memory_size))
+
+
+def run_both3(om_fn, setup, kernels, tag, fill, rtol=0.0):
+    desc, so = build_emulated(setup, om_fn(), tag=tag)
+    assert desc["dim"] == 3
+    m = Machine(desc, so, device="cpu", _emulated=True)
+    o = OracleMachine(setup, om_fn())
+    for name, arr in fill.items():
+        m.set(name, arr, with_margin=True)
+        o.array(name)[...] = arr
+    for k in kernels:
+        m.call(k); o.call(k)
+        for s in desc["statics"]:
+            if s["realm"] == "Array":
+                a, b = m.get(s["name"], with_margin=True), o.array(s["name"])
+                assert a.shape == b.shape
+                if rtol:
+                    assert np.allclose(a, b, rtol=rtol, atol=0), (k, s["name"])
+                else:
+                    assert np.array_equal(a, b), (k, s["name"])
+            else:
+                a, b = m.scalar(s["name"]), o.scalar(s["name"])[0]
+                assert (abs(a - b) <= rtol * abs(b)) if rtol else (a == b), (k, s["name"])
+    return m, o
+
+
+def life3d_om():
+    """26-neighbour life on a rank-3 grid (rule 5..7 survive / 6 born), population reduce, generation counter."""
+    cell = Named("cell", StaticValue(ARRAY, "Int"))
+    pop = Named("population", StaticValue(SCALAR, "Int"))
+    gen = Named("generation", StaticValue(SCALAR, "Int"))
+
+    def proceed():
+        c = bind(load(cell))
+        nb = [shift((dx, dy, dz), c) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)]
+        num = bind(sum_(nb))
+        alive = bind((eq(c, 0) & eq(num, 6)) | (eq(c, 1) & ge(num, 5) & le(num, 7)))
+        new = bind(select(alive, imm(1, ARRAY, "Int"), 0))
+        store(cell, new)
+        store(pop, reduce("Sum", new))
+        store(gen, load(gen) + 1)
+    return makeOM("Life3", [], [cell, pop, gen], [("proceed", proceed)], dim=3)
+
+
+@pytest.mark.parametrize("bnd,size", [((CYCLIC, CYCLIC, CYCLIC), (37, 11, 6)), ((OPEN, CYCLIC, OPEN), (20, 9, 5)),
+                                      ((CYCLIC, OPEN, CYCLIC), (130, 7, 3)), ((CYCLIC, CYCLIC, CYCLIC), (5, 4, 1))])
+def test_life3d_bit_exact(bnd, size):
+    setup = Setup(local_size=size, boundary=bnd)
+    fill = {"cell": (np.random.default_rng(11).random(mem_shape3(setup, life3d_om)) < 0.3).astype(np.int32)}
+    run_both3(life3d_om, setup, ["proceed"] * 3, f"life3d_{''.join(b[0] for b in bnd)}", fill)
+
+
+def diffusion3d_om():
+    """7-point diffusion with a position-dependent source (loadIndex of all three axes, loadSize), an intermediate that
+    is worth a shared-memory ring, an asymmetric axis-2 reach and a Max reduce feeding a second stage."""
+    u = Named("u", StaticValue(ARRAY, "Double"))
+    peak = Named("peak", StaticValue(SCALAR, "Double"))
+
+    def init():
+        x, y, z = (cast(loadIndex(a), "Double") for a in range(3))
+        n2 = broadcast(cast(loadSize(2), "Double"))
+        store(u, (x * 0.25 + y * y * 0.125 - z) / (n2 + 1.0))
+
+    def proceed():
+        x = bind(load(u))
+        g = bind(sqrt(x * x + 2.0) / (3.0 + x * x))                      # materialised along axes 0 / 1, recomputed across planes
+        lap = bind(shift((1, 0, 0), g) + shift((-1, 0, 0), g) + shift((0, 1, 0), g) + shift((0, -1, 0), g) +
+                   shift((0, 0, 1), g) + shift((0, 0, -2), g) - 6 * g)
+        new = bind(x + 0.05 * lap + 1e-3 * cast(loadIndex(2), "Double"))
+        mx = bind(reduce("Max", new))
+        store(peak, mx)
+        store(u, new / (broadcast(mx) + 1.0))
+    return makeOM("Diff3", [], [u, peak], [("init", init), ("proceed", proceed)], dim=3)
+
+
+@pytest.mark.parametrize("bnd", [(OPEN, OPEN, OPEN), (CYCLIC, OPEN, CYCLIC)])
+def test_diffusion3d_bit_identical(bnd):
+    setup = Setup(local_size=(70, 12, 7), boundary=bnd)
+    run_both3(diffusion3d_om, setup, ["init", "proceed", "proceed"], f"diff3d_{''.join(b[0] for b in bnd)}", {})
