@@ -173,7 +173,11 @@ class StageEmitter:
         if not self.dim3:
             return f"in{sidx}"
         nm = f"inz{v}"
-        self.zdefs[nm] = f"const {self.T(v)}* __restrict__ {nm} = in{sidx} + (ptrdiff_t)(zp + ({self.zoff_of[v]})) * g.plane;"
+        z = self.zoff_of[v]
+        # planes beyond the stack are only asked for by cells outside the Valid region (Open axis 2), whose results
+        # are masked: clamp instead of reading outside the allocation
+        zexpr = "zp" if z == 0 else f"min(max(zp + ({z}), 0), g.nz + g.gz_lo + g.gz_hi - 1)"
+        self.zdefs[nm] = f"const {self.T(v)}* __restrict__ {nm} = in{sidx} + (ptrdiff_t)({zexpr}) * g.plane;"
         return nm
 
     def outp(self, s: int, T: str) -> str:

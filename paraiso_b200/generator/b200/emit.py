@@ -127,9 +127,8 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     files = [(f"{om.name}_kernels.cu", "\n".join(cu) + "\n"),
              (f"{om.name}_abi.json", json.dumps(desc, indent=1) + "\n"),
              ("om_runtime.cuh", runtime)]
-    from .host import emit_abi_header, emit_host
-    # (the C++ host class is emitted for rank 1 and 2; rank-3 machines are driven through the C ABI, e.g. runtime.Machine)
-    files += emit_host(desc) if setup.dim <= 2 else [(f"{om.name}_abi.h", emit_abi_header(desc))]
+    from .host import emit_host
+    files += emit_host(desc)
     return files
 
 

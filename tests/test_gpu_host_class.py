@@ -114,3 +114,38 @@ def test_cpp_class_rejects_more_gpus_than_visible():
     exe = build_driver("Life", "Life_CC", "life_driver.cpp")
     r = subprocess.run([exe, "1"], capture_output=True, text=True, env=dict(os.environ, OM_B200_GPUS="64"))
     assert r.returncode != 0 and "OM_B200_GPUS" in r.stderr
+
+
+def test_rank3_cpp_class_matches_oracle():
+    """The generated class of a rank-3 machine: `cell(x, y, z)` accessors, plane-wise mirror copies, ghost planes."""
+    from oracle.cpu import OracleMachine
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.rank3 import life3d_om
+    from paraiso_b200.generator.native import Setup
+    setup = Setup(local_size=(48, 20, 12), boundary=("Cyclic", "Cyclic", "Cyclic"))
+    build_machine(setup, life3d_om(), tag="Life3_host")
+    steps = 5
+    exe = build_driver("Life3", "Life3_host", "life3_driver.cpp")
+    out = subprocess.run([exe, str(steps)], check=True, capture_output=True, text=True).stdout.split("\n")
+    W, H, D, gen, total, hsh = (int(v) for v in out[0].split())
+    o = OracleMachine(setup, life3d_om())
+    c = o.interior("cell")
+    s = 20261017
+    for z in range(D):
+        for y in range(H):
+            for x in range(W):
+                s = (s * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+                if (s >> 33) % 100 < 30:
+                    c[z, y, x] = 1
+    pop = None
+    for t in range(steps):
+        o.call("proceed")
+        pop = int(o.scalar("population")[0])
+        if t == 2:
+            o.interior("cell")[t % D, t % H, t % W] = 1
+    cells = o.interior("cell")
+    h = 1469598103934665603
+    for v in cells.ravel():
+        h = ((h ^ int(v)) * 1099511628211) % (1 << 64)
+    assert (gen, total, hsh) == (steps, int(cells.sum()), h)
+    assert out[1] == f"population {pop}"

@@ -7,9 +7,7 @@ import pytest
 from oracle.cpu import OracleMachine
 from paraiso_b200.annotation import CYCLIC, OPEN
 from paraiso_b200.generator.native import Setup
-from paraiso_b200.om.builder import (StaticValue, bind, broadcast, cast, imm, load, loadIndex, loadSize, makeOM, reduce, select, shift,
-                                     store, eq, ge, le, sqrt, sum_)
-from paraiso_b200.om.graph import ARRAY, SCALAR, Named
+from paraiso_b200.examples.rank3 import diffusion3d_om, life3d_om
 from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
@@ -44,53 +42,12 @@ def run_both3(om_fn, setup, kernels, tag, fill, rtol=0.0):
     return m, o
 
 
-def life3d_om():
-    """26-neighbour life on a rank-3 grid (rule 5..7 survive / 6 born), population reduce, generation counter."""
-    cell = Named("cell", StaticValue(ARRAY, "Int"))
-    pop = Named("population", StaticValue(SCALAR, "Int"))
-    gen = Named("generation", StaticValue(SCALAR, "Int"))
-
-    def proceed():
-        c = bind(load(cell))
-        nb = [shift((dx, dy, dz), c) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)]
-        num = bind(sum_(nb))
-        alive = bind((eq(c, 0) & eq(num, 6)) | (eq(c, 1) & ge(num, 5) & le(num, 7)))
-        new = bind(select(alive, imm(1, ARRAY, "Int"), 0))
-        store(cell, new)
-        store(pop, reduce("Sum", new))
-        store(gen, load(gen) + 1)
-    return makeOM("Life3", [], [cell, pop, gen], [("proceed", proceed)], dim=3)
-
-
 @pytest.mark.parametrize("bnd,size", [((CYCLIC, CYCLIC, CYCLIC), (37, 11, 6)), ((OPEN, CYCLIC, OPEN), (20, 9, 5)),
                                       ((CYCLIC, OPEN, CYCLIC), (130, 7, 3)), ((CYCLIC, CYCLIC, CYCLIC), (5, 4, 1))])
 def test_life3d_bit_exact(bnd, size):
     setup = Setup(local_size=size, boundary=bnd)
     fill = {"cell": (np.random.default_rng(11).random(mem_shape3(setup, life3d_om)) < 0.3).astype(np.int32)}
     run_both3(life3d_om, setup, ["proceed"] * 3, f"life3d_{''.join(b[0] for b in bnd)}", fill)
-
-
-def diffusion3d_om():
-    """7-point diffusion with a position-dependent source (loadIndex of all three axes, loadSize), an intermediate that
-    is worth a shared-memory ring, an asymmetric axis-2 reach and a Max reduce feeding a second stage."""
-    u = Named("u", StaticValue(ARRAY, "Double"))
-    peak = Named("peak", StaticValue(SCALAR, "Double"))
-
-    def init():
-        x, y, z = (cast(loadIndex(a), "Double") for a in range(3))
-        n2 = broadcast(cast(loadSize(2), "Double"))
-        store(u, (x * 0.25 + y * y * 0.125 - z) / (n2 + 1.0))
-
-    def proceed():
-        x = bind(load(u))
-        g = bind(sqrt(x * x + 2.0) / (3.0 + x * x))                      # materialised along axes 0 / 1, recomputed across planes
-        lap = bind(shift((1, 0, 0), g) + shift((-1, 0, 0), g) + shift((0, 1, 0), g) + shift((0, -1, 0), g) +
-                   shift((0, 0, 1), g) + shift((0, 0, -2), g) - 6 * g)
-        new = bind(x + 0.05 * lap + 1e-3 * cast(loadIndex(2), "Double"))
-        mx = bind(reduce("Max", new))
-        store(peak, mx)
-        store(u, new / (broadcast(mx) + 1.0))
-    return makeOM("Diff3", [], [u, peak], [("init", init), ("proceed", proceed)], dim=3)
 
 
 @pytest.mark.parametrize("bnd", [(OPEN, OPEN, OPEN), (CYCLIC, OPEN, CYCLIC)])
