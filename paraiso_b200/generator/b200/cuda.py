@@ -176,7 +176,7 @@ class StageEmitter:
         z = self.zoff_of[v]
         # planes beyond the stack are only asked for by cells outside the Valid region (Open axis 2), whose results
         # are masked: clamp instead of reading outside the allocation
-        zexpr = "zp" if z == 0 else f"min(max(zp + ({z}), 0), g.nz + g.gz_lo + g.gz_hi - 1)"
+        zexpr = "zp" if z == 0 else f"min(max(zp + ({z}), 0), g.nzl + g.gz_lo + g.gz_hi - 1)"
         self.zdefs[nm] = f"const {self.T(v)}* __restrict__ {nm} = in{sidx} + (ptrdiff_t)({zexpr}) * g.plane;"
         return nm
 
@@ -411,7 +411,7 @@ class StageEmitter:
                     elif ax == 1:
                         lines.append(f"const int {nm} = g.cyc_y ? om_wrap(row + ({cur[1]}) - g.yorg + g.y0, g.ny) : (row + ({cur[1]}) - g.yorg + g.y0);")
                     else:      # axis 2: the CTA's plane plus the offset lower_z gave this node
-                        lines.append(f"const int {nm} = g.cyc_z ? om_wrap(zp + ({op.zoff}) - g.zorg, g.nz) : (zp + ({op.zoff}) - g.zorg);")
+                        lines.append(f"const int {nm} = g.cyc_z ? om_wrap(zp + ({op.zoff}) - g.zorg + g.z0, g.nz) : (zp + ({op.zoff}) - g.zorg + g.z0);")
                 e = f"(({T}){nm})"
             elif op.kind == "LoadSize":
                 e = f"(({T}){('g.nx', 'g.ny', 'g.nz')[op.inst.arg]})"
@@ -698,7 +698,7 @@ class StageEmitter:
                 conds_row.append(f"(gmy >= {lby}) && (gmy < memy - {uby})")
             lbz, ubz = self.valid_box_z(v)
             if lbz or ubz:
-                P(f"const int gmz = zp - g.zorg + {self.margin_lo[2]}, memz = g.nz + {self.margin_lo[2] + self.margin_hi[2]};   // plane in the reference memory box")
+                P(f"const int gmz = zp - g.zorg + g.z0 + {self.margin_lo[2]}, memz = g.nz + {self.margin_lo[2] + self.margin_hi[2]};   // plane in the reference memory box")
                 conds_row.append(f"(gmz >= {lbz}) && (gmz < memz - {ubz})")
             for k in range(V):
                 conds = list(conds_row)

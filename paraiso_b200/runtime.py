@@ -40,7 +40,7 @@ class OmGeom(ctypes.Structure):
         "nx", "ny", "pitch", "rows", "xorg", "yorg", "y0", "nyl",
         "gx_lo", "gx_hi", "gy_lo", "gy_hi", "cyc_x", "cyc_y", "wrap_y_local",
         "own_r0", "own_r1", "chunk_rows", "red_accumulate",
-        "nz", "plane", "zorg", "gz_lo", "gz_hi", "cyc_z", "own_z0", "own_z1")]
+        "nz", "plane", "zorg", "gz_lo", "gz_hi", "cyc_z", "own_z0", "own_z1", "z0", "nzl")]
 
 
 def _ru(x, m):
@@ -74,8 +74,6 @@ class Machine:
         self.dim3 = desc["dim"] == 3
         if not self.dim3 and self.nz != 1:
             raise ValueError("a rank-2 machine takes a (nx, ny) size")
-        if self.dim3 and nranks > 1:
-            raise NotImplementedError("rank-3 machines run on one GPU (the slab decomposition splits axis 1 of rank-2 machines)")
         pad3 = lambda t, fill: list(t) + [fill] * (3 - len(t))
         self.boundary = pad3(desc["boundary"], "Open")
         self.mlo, self.mhi = pad3(desc["lower_margin"], 0), pad3(desc["upper_margin"], 0)
@@ -84,15 +82,18 @@ class Machine:
         for ax in range(3):
             if not self.cyc[ax]:
                 assert self.mlo[ax] == rlo[ax] and self.mhi[ax] == rhi[ax], "Open margins must equal the stencil radius"
-        self.y0, self.nyl = slab_rows(self.ny, nranks, rank)
-        if nranks > 1 and self.nyl < max(rlo[1], rhi[1]):
+        # the slab decomposition cuts the outermost axis: axis 1 of rank-1 / rank-2 machines (rows are contiguous), axis 2 of
+        # rank-3 machines (whole planes are contiguous)
+        self.y0, self.nyl = (0, self.ny) if self.dim3 else slab_rows(self.ny, nranks, rank)
+        self.z0, self.nzl = slab_rows(self.nz, nranks, rank) if self.dim3 else (0, 1)
+        if nranks > 1 and (self.nzl < max(rlo[2], rhi[2]) if self.dim3 else self.nyl < max(rlo[1], rhi[1])):
             raise ValueError("slab thinner than the stencil radius")
         self.gx_lo, self.gx_hi, self.gy_lo, self.gy_hi = rlo[0], rhi[0], rlo[1], rhi[1]
         self.xorg = _ru(max(self.gx_lo, 1), 32)
         self.pitch = _ru(self.xorg + self.nx + self.gx_hi, 32)
         self.yorg = self.gy_lo
         self.rows = self.nyl + self.gy_lo + self.gy_hi
-        first, last = rank == 0, rank == nranks - 1
+        first, last = (rank == 0, rank == nranks - 1) if not self.dim3 else (True, True)
         if self.cyc[1]:
             self.own_r0, self.own_r1 = self.yorg, self.yorg + self.nyl
         else:
@@ -102,8 +103,12 @@ class Machine:
         # rank 3: planes of rows * pitch elements stacked along axis 2 (ghost planes included); rank 2: one plane
         self.gz_lo, self.gz_hi = rlo[2], rhi[2]
         self.zorg = self.gz_lo
-        self.planes = self.nz + self.gz_lo + self.gz_hi
-        self.own_z0, self.own_z1 = (self.zorg, self.zorg + self.nz) if self.cyc[2] else (0, self.planes)
+        self.planes = self.nzl + self.gz_lo + self.gz_hi
+        if self.cyc[2]:
+            self.own_z0, self.own_z1 = self.zorg, self.zorg + self.nzl
+        else:      # Open: the end ranks also own the reference's margin planes
+            self.own_z0 = 0 if rank == 0 else self.zorg
+            self.own_z1 = self.planes if rank == nranks - 1 else self.zorg + self.nzl
         # storage
         self.statics = desc["statics"]
         self.index = {s["name"]: i for i, s in enumerate(self.statics)}
@@ -198,10 +203,10 @@ class Machine:
         g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
                    cyc_x=int(self.cyc[0]), cyc_y=int(self.cyc[1]),
-                   wrap_y_local=int(self.cyc[1] and self.nranks == 1),
+                   wrap_y_local=int(self.cyc[1] and (self.nranks == 1 or self.dim3)),
                    own_r0=r0, own_r1=r1, chunk_rows=max(1, chunk_rows), red_accumulate=int(accumulate),
                    nz=self.nz, plane=(self.rows * self.pitch if self.dim3 else 0), zorg=self.zorg, gz_lo=self.gz_lo,
-                   gz_hi=self.gz_hi, cyc_z=int(self.cyc[2]), own_z0=self.own_z0, own_z1=self.own_z1)
+                   gz_hi=self.gz_hi, cyc_z=int(self.cyc[2]), own_z0=self.own_z0, own_z1=self.own_z1, z0=self.z0, nzl=self.nzl)
         if strips * (-(-nrows // max(1, chunk_rows))) * (self.own_z1 - self.own_z0) > self.max_blocks:
             raise ValueError("grid too large for the reduction scratch")
         self._geom_cache[key] = g
@@ -245,7 +250,7 @@ class Machine:
             # (light streaming stages only: for a heavy stage the two boundary launches pay the full pipeline
             #  warm-up for a handful of rows, which costs more than the ~20 us exchange they would hide)
             if (last_storing and self.device.type == "cuda" and self.overlap and st.get("chunk_rows", 0) > 0
-                    and self.nyl >= 4 * max(self.gy_lo, self.gy_hi, 1)):
+                    and not self.dim3 and self.nyl >= 4 * max(self.gy_lo, self.gy_hi, 1)):
                 # boundary rows first, then their exchange on a side stream (NCCL send/recv) while the interior
                 # of the slab is computed on the compute stream
                 lo_rows = (self.own_r0, self.yorg + self.gy_hi)                       # rows the lower neighbour needs
@@ -284,7 +289,7 @@ class Machine:
             self.launches += 1
         for s in stores:
             self.cur[s], self.alt[s] = self.alt[s], self.cur[s]
-            if self.dim3 and self.cyc[2]:
+            if self.dim3 and self.cyc[2] and self.nranks == 1:
                 self._fill_z_ghosts(self.cur[s])     # whole planes (their x / y ghost cells were written by the kernel)
         self._refresh_ptrs()
         if self.nranks > 1 and not overlapped:
@@ -319,22 +324,26 @@ class Machine:
             pass
 
     def _exchange_rows(self, a: torch.Tensor):
-        """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too)."""
+        """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too).  Rank-3 machines are cut
+        along axis 2: whole ghost planes travel (their x / y ghost cells included)."""
         import torch.distributed as dist
         n, r = self.nranks, self.rank
         up, down = (r + 1) % n, (r - 1) % n
-        has_up = self.cyc[1] or r < n - 1
-        has_down = self.cyc[1] or r > 0
+        if self.dim3:
+            a, g_lo, g_hi, y0, y1, cyc = self._v3(a), self.gz_lo, self.gz_hi, self.zorg, self.zorg + self.nzl, self.cyc[2]
+        else:
+            g_lo, g_hi, y0, y1, cyc = self.gy_lo, self.gy_hi, self.yorg, self.yorg + self.nyl, self.cyc[1]
+        has_up = cyc or r < n - 1
+        has_down = cyc or r > 0
         ops = []
-        y0, y1 = self.yorg, self.yorg + self.nyl
-        if self.gy_lo and has_up:     # my top interior rows are the upper neighbour's lower ghost rows
-            ops.append(dist.P2POp(dist.isend, a[y1 - self.gy_lo:y1], up, group=self.group))
-        if self.gy_hi and has_down:   # my bottom interior rows are the lower neighbour's upper ghost rows
-            ops.append(dist.P2POp(dist.isend, a[y0:y0 + self.gy_hi], down, group=self.group))
-        if self.gy_lo and has_down:
-            ops.append(dist.P2POp(dist.irecv, a[0:self.gy_lo], down, group=self.group))
-        if self.gy_hi and has_up:
-            ops.append(dist.P2POp(dist.irecv, a[y1:y1 + self.gy_hi], up, group=self.group))
+        if g_lo and has_up:     # my top interior rows are the upper neighbour's lower ghost rows
+            ops.append(dist.P2POp(dist.isend, a[y1 - g_lo:y1], up, group=self.group))
+        if g_hi and has_down:   # my bottom interior rows are the lower neighbour's upper ghost rows
+            ops.append(dist.P2POp(dist.isend, a[y0:y0 + g_hi], down, group=self.group))
+        if g_lo and has_down:
+            ops.append(dist.P2POp(dist.irecv, a[0:g_lo], down, group=self.group))
+        if g_hi and has_up:
+            ops.append(dist.P2POp(dist.irecv, a[y1:y1 + g_hi], up, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -346,7 +355,7 @@ class Machine:
     def _fill_z_ghosts(self, a: torch.Tensor):
         """Rank 3, Cyclic axis 2: ghost planes <- the interior planes they wrap to (contiguous device copies)."""
         a3 = self._v3(a)
-        z0, z1 = self.zorg, self.zorg + self.nz
+        z0, z1 = self.zorg, self.zorg + self.nzl
         if self.gz_lo:
             a3[0:self.gz_lo] = a3[z1 - self.gz_lo:z1]
         if self.gz_hi:
@@ -368,7 +377,9 @@ class Machine:
                     a3[:, 0:self.gy_lo] = a3[:, y1 - self.gy_lo:y1]
                 if self.gy_hi:
                     a3[:, y1:y1 + self.gy_hi] = a3[:, y0:y0 + self.gy_hi]
-            if self.cyc[2]:
+            if self.nranks > 1:
+                self._exchange_rows(a)
+            elif self.cyc[2]:
                 self._fill_z_ghosts(a)
             return
         x0, x1 = self.xorg, self.xorg + self.nx
@@ -391,7 +402,7 @@ class Machine:
         """(plane, row, column) slices of the interior, or of the part of the reference's memory box this rank owns."""
         if with_margin:
             return slice(self.own_z0, self.own_z1), slice(self.own_r0, self.own_r1), slice(self.cx0, self.cx1)
-        return (slice(self.zorg, self.zorg + self.nz), slice(self.yorg, self.yorg + self.nyl),
+        return (slice(self.zorg, self.zorg + self.nzl), slice(self.yorg, self.yorg + self.nyl),
                 slice(self.xorg, self.xorg + self.nx))
 
     def get(self, name: str, with_margin: bool = False) -> np.ndarray:

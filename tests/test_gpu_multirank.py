@@ -20,7 +20,18 @@ def _worker(rank, world, port, which, size, steps, ret):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from paraiso_b200.machines import hydro_machine, hydro_set_params, life_machine, life_seed
-    if which == "life":
+    if which == "diff3":
+        from paraiso_b200.build import build_machine
+        from paraiso_b200.examples.rank3 import diffusion3d_om
+        from paraiso_b200.generator.native import Setup
+        from paraiso_b200.runtime import Machine
+        desc, so = build_machine(Setup(local_size=size, boundary=("Cyclic", "Open", "Open")), diffusion3d_om(), tag="Diff3_COO")
+        m = Machine(desc, so, size=size, device=dev, rank=rank, nranks=world)
+        m.call("init")
+        for _ in range(steps):
+            m.call("proceed")
+        ret[rank] = (m.z0, m.get("u"), float(m.scalar("peak")))
+    elif which == "life":
         m = life_machine(size, device=dev, rank=rank, nranks=world)
         m.call("init")
         m.set("cell", life_seed(size[0], m.y0, m.nyl, nx_global=size[0]))
@@ -74,3 +85,22 @@ def test_hydro_two_gpus_equal_one_gpu():
         two = np.concatenate([p[1][n] for p in parts], axis=0)
         assert np.array_equal(m.get(n).view(np.uint64), two.view(np.uint64)), n
     assert all(p[2] == float(m.scalar("time")) for p in parts)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rank3_two_gpus_equal_one_gpu():
+    """Rank-3 machines are cut along axis 2: ghost planes by NCCL send/recv, the Max reduce by all_reduce."""
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.rank3 import diffusion3d_om
+    from paraiso_b200.generator.native import Setup
+    from paraiso_b200.runtime import Machine
+    size, steps = (200, 48, 37), 5
+    desc, so = build_machine(Setup(local_size=size, boundary=("Cyclic", "Open", "Open")), diffusion3d_om(), tag="Diff3_COO")
+    m = Machine(desc, so, size=size)
+    m.call("init")
+    for _ in range(steps):
+        m.call("proceed")
+    parts = _multi("diff3", size, steps, 29715)
+    two = np.concatenate([p[1] for p in parts], axis=0)
+    assert np.array_equal(m.get("u").view(np.uint64), two.view(np.uint64))
+    assert all(p[2] == float(m.scalar("peak")) for p in parts)

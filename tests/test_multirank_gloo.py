@@ -111,3 +111,51 @@ def test_hydro_carried_dt_reduce_two_ranks():
         f2 = np.concatenate([p[1][n] for p in parts], axis=0)
         assert np.array_equal(f1[n].view(np.uint64), f2.view(np.uint64)), n
     assert all(p[2] == t1 for p in parts)
+
+
+def _worker3(rank, world, port, which, size, steps, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ret[rank] = _rank3_run(which, size, steps, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _rank3_run(which, size, steps, rank, world):
+    from paraiso_b200.examples.rank3 import diffusion3d_om, life3d_om
+    from paraiso_b200.generator.native import Setup
+    from paraiso_b200.runtime import Machine
+    from tests.emu.build_emu import build_emulated
+    if which == "life3":
+        setup = Setup(local_size=size, boundary=("Cyclic", "Cyclic", "Cyclic"))
+        desc, so = build_emulated(setup, life3d_om(), tag="life3d_CCC")
+        m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
+        full = (np.random.default_rng(3).random((size[2], size[1], size[0])) < 0.3).astype(np.int32)
+        m.set("cell", full[m.z0:m.z0 + m.nzl])
+        for _ in range(steps):
+            m.call("proceed")
+        return m.z0, m.get("cell"), int(m.scalar("population"))
+    setup = Setup(local_size=size, boundary=("Open", "Open", "Open"))
+    desc, so = build_emulated(setup, diffusion3d_om(), tag="diff3d_OOO")
+    m = Machine(desc, so, size=size, device="cpu", rank=rank, nranks=world, _emulated=True)
+    m.call("init")
+    for _ in range(steps):
+        m.call("proceed")
+    return m.z0, m.get("u"), float(m.scalar("peak"))
+
+
+@pytest.mark.parametrize("which,size", [("life3", (37, 9, 11)), ("diff3", (40, 10, 13))])
+def test_rank3_slabs_along_axis2_equal_one_rank(which, size):
+    """Rank-3 machines are cut along axis 2: ghost planes travel, loadIndex(2) carries the slab offset, the Max / Sum
+    reduces are all_reduced (3 ranks: uneven slabs, a middle rank without physical margins)."""
+    steps = 3
+    _z, a1, s1 = _rank3_run(which, size, steps, 0, 1)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker3, args=(3, 29651 + (which == "diff3"), which, size, steps, ret), nprocs=3, join=True)
+    parts = sorted([ret[r] for r in range(3)], key=lambda p: p[0])
+    a3 = np.concatenate([p[1] for p in parts], axis=0)
+    assert np.array_equal(a1.view(np.uint8), a3.view(np.uint8))
+    assert all(p[2] == s1 for p in parts)
