@@ -48,3 +48,15 @@ def diffusion3d_om():
         store(peak, mx)
         store(u, new / (broadcast(mx) + 1.0))
     return makeOM("Diff3", [], [u, peak], [("init", init), ("proceed", proceed)], dim=3)
+
+
+def heat3d_om(real: str = "Float"):
+    """7-point explicit heat equation u += k * laplacian(u): the lightest rank-3 stencil (bandwidth test)."""
+    u = Named("u", StaticValue(ARRAY, real))
+
+    def proceed():
+        x = bind(load(u))
+        lap = bind(shift((1, 0, 0), x) + shift((-1, 0, 0), x) + shift((0, 1, 0), x) + shift((0, -1, 0), x) +
+                   shift((0, 0, 1), x) + shift((0, 0, -1), x) - 6 * x)
+        store(u, x + 0.1 * lap)
+    return makeOM("Heat3", [], [u], [("proceed", proceed)], dim=3)

@@ -260,6 +260,7 @@ class StageBuilder:
         self.ops, self.dim, self.stage = ops, dim, stage
         self.mat_threshold = mat_threshold
         self.mat_flip = set(mat_flip)          # value ids whose materialise / recompute decision is inverted
+        self.stage_z_inputs = True
         self.candidates: List[dict] = []       # every shifted value with its cost and decision (for the schedule search)
 
     # -- closure of array nodes needed by the stage (through shifts), and scalar roots
@@ -407,7 +408,9 @@ class StageBuilder:
                 op = ops[b]
                 # through shared memory only when another thread's columns are read; same-column reads
                 # at several rows are plain (L1/L2-resident) global loads
-                via = any(c[0] != 0 for (_n, c) in d["uses"])
+                # (rank 3: the neighbouring planes' rows are staged too — they come from L2 / HBM with the same latency
+                #  as the centre plane's, and the staging pipeline is what hides it)
+                via = any(c[0] != 0 for (_n, c) in d["uses"]) or (op.zoff != 0 and self.stage_z_inputs)
                 st.inputs[b] = InputArr(static_idx=op.inst.arg, vid=b, ctype=op.ctype, lag=lag[b], depth=d["depth"],
                                         via_smem=via, xlo=xlo[b], xhi=xhi[b], early=early[b],
                                         rd_xlo=d["rd_xlo"], rd_xhi=d["rd_xhi"], zoff=op.zoff)
