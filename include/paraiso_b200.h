@@ -37,7 +37,8 @@
  * Rank-3 machines (ABI version 2) stack `nz + gz_lo + gz_hi` planes of `rows * pitch` elements along axis 2
  * (`plane` = that stride, interior plane 0 at device plane `zorg`; the aprons surround the whole stack); a launch
  * covers device planes [own_z0, own_z1) with one layer of CTAs per plane, and the host copies the ghost planes of a
- * Cyclic axis 2 after each store.  Rank-1 / rank-2 callers pass nz = 1, plane = 0, own_z0 = 0, own_z1 = 1.
+ * Cyclic axis 2 after each store; with several ranks the slab is cut along axis 2 (`z0` = global index of local plane 0,
+ * `nzl` local planes).  Rank-1 / rank-2 callers pass nz = 1, plane = 0, own_z0 = 0, own_z1 = 1, z0 = 0, nzl = 1.
  */
 #pragma once
 #include "om_Life_abi.h"
