@@ -18,7 +18,7 @@ def test_life3d_bit_exact(bnd, size):
     from paraiso_b200.examples.rank3 import life3d_om
     from paraiso_b200.generator.native import Setup
     setup = Setup(local_size=size, boundary=bnd)
-    m, o = _pair(life3d_om, setup, f"Life3_{''.join(b[0] for b in bnd)}")
+    m, o = _pair(life3d_om, setup, f"Life3_t_{''.join(b[0] for b in bnd)}")
     init = (np.random.default_rng(5).random(o.array("cell").shape) < 0.3).astype(np.int32)
     m.set("cell", init, with_margin=True)
     o.array("cell")[...] = init
@@ -34,7 +34,7 @@ def test_diffusion3d_bit_identical(bnd):
     from paraiso_b200.examples.rank3 import diffusion3d_om
     from paraiso_b200.generator.native import Setup
     setup = Setup(local_size=(260, 41, 19), boundary=bnd)
-    m, o = _pair(diffusion3d_om, setup, f"Diff3_{''.join(b[0] for b in bnd)}")
+    m, o = _pair(diffusion3d_om, setup, f"Diff3_t_{''.join(b[0] for b in bnd)}")
     m.call("init"); o.call("init")
     for t in range(4):
         m.call("proceed"); o.call("proceed")

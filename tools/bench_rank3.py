@@ -17,7 +17,7 @@ def heat(n):
     from paraiso_b200.examples.rank3 import heat3d_om
     size = (n, n, n)
     setup = Setup(local_size=size, boundary=("Cyclic", "Cyclic", "Cyclic"))
-    desc, so = build_machine(setup, heat3d_om(), tag="Heat3_CCC")
+    desc, so = build_machine(setup, heat3d_om(), tag="Heat3_bench")
     m = Machine(desc, so, size=size)
     m.set("u", torch.rand((n, n, n), dtype=torch.float32).numpy())
     ms = measure(m, "proceed", steps=20, warmup=3)
@@ -33,7 +33,7 @@ if __name__ == "__main__":
         sys.exit(0)
     size = (n, n, n)
     setup = Setup(local_size=size, boundary=("Cyclic", "Cyclic", "Cyclic"))
-    desc, so = build_machine(setup, life3d_om(), tag="Life3_CCC")
+    desc, so = build_machine(setup, life3d_om(), tag="Life3_bench")
     m = Machine(desc, so, size=size)
     g = torch.Generator(device="cuda").manual_seed(1)
     init = (torch.rand((n, n, n), device="cuda", generator=g) < 0.3).to(torch.int32)
