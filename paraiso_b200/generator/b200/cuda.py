@@ -454,7 +454,7 @@ class StageEmitter:
         om = self.om
         self.pre_names = set()
         in_statics = sorted({i.static_idx for i in st.inputs.values()})
-        out_statics = [s for (s, _v) in st.store_targets]
+        out_statics = list(dict.fromkeys(s for (s, _v) in st.store_targets))
         sv = om.setup.static_values
         params = ["const OmGeom g"]
         for s in in_statics:
@@ -599,7 +599,7 @@ class StageEmitter:
         E("  const int r1 = min(r0 + g.chunk_rows, g.own_r1);")
         E(f"  const int jbeg = r0 - {lead};")
         if self.dim3:
-            E("  const int zp = g.own_z0 + blockIdx.z;                 // this CTA's plane of axis 2 (device plane index)")
+            E(f"  const int zp = g.own_z0 + blockIdx.z * {st.zplanes};   // this CTA's (first) plane of axis 2 (device plane index)")
             for l in self.zdefs.values():
                 E("  " + l)
         for l in self.scalar_code(list(dict.fromkeys(st.scalar_roots))):
@@ -608,7 +608,7 @@ class StageEmitter:
             E("  " + l)
         for l in self.pre:
             E("  " + l)
-        for (v, rop, slot) in st.reduce_targets + st.carried:
+        for (v, rop, slot) in self.reduce_slots_once():
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
@@ -672,7 +672,15 @@ class StageEmitter:
         per-lane predicates are only evaluated on the rare partial-vector path."""
         st, V = self.st, self.V
         B: List[str] = []
-        targets = list(dict.fromkeys([v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]))
+        Z = st.zplanes
+        splane = lambda s_, v_: st.store_plane.get((s_, v_), 0)
+        rplane = lambda n: st.reduce_plane[n] if n < len(st.reduce_plane) else 0
+        # (value, plane offset inside the CTA's group of Z planes) of everything this row stores or reduces
+        entries = list(dict.fromkeys([(v, splane(s_, v)) for (s_, v) in st.store_targets] +
+                                     [(v, rplane(n)) for n, (v, _o, _k) in enumerate(st.reduce_targets)]))
+        targets = list(dict.fromkeys(v for (v, _zo) in entries))
+        oname = (lambda v_, zo_, k_: f"o{v_}_{k_}") if Z == 1 else (lambda v_, zo_, k_: f"o{v_}z{zo_}_{k_}")
+        zlive = lambda zo_: None if zo_ == 0 else f"zlive{zo_}"
         mly, mhy = self.margin_lo[1], self.margin_hi[1]
 
         def P(line):
@@ -689,7 +697,9 @@ class StageEmitter:
         lines, res = self.scope(targets, 0)
         B += ["  " + l for l in lines]
         need_gmy = False
-        for v in targets:
+        for zo in sorted({zo_ for (_v, zo_) in entries if zo_ > 0}):
+            P(f"const bool zlive{zo} = zp + {zo} < g.own_z1;   // the last group of planes may be incomplete")
+        for (v, zo) in entries:
             lbx, ubx, lby, uby = self.valid_box(v)
             T = self.T(v)
             conds_row = []
@@ -699,7 +709,7 @@ class StageEmitter:
             lbz, ubz = self.valid_box_z(v)
             if lbz or ubz:
                 P(f"const int gmz = zp - g.zorg + g.z0 + {self.margin_lo[2]}, memz = g.nz + {self.margin_lo[2] + self.margin_hi[2]};   // plane in the reference memory box")
-                conds_row.append(f"(gmz >= {lbz}) && (gmz < memz - {ubz})")
+                conds_row.append(f"(gmz + {zo} >= {lbz}) && (gmz + {zo} < memz - {ubz})")
             for k in range(V):
                 conds = list(conds_row)
                 if lbx or ubx:
@@ -707,19 +717,23 @@ class StageEmitter:
                     P(f"const bool {hn} = (tc + {k} >= cx0 + {lbx}) && (tc + {k} < cx1 - {ubx});")
                     conds.append(hn)
                 if conds:   # cells of the memory box outside the Valid region are never written by the reference: they stay 0
-                    B.append(f"  const {T} o{v}_{k} = ({' && '.join(conds)}) ? {res[(v, k)]} : ({T})0;")
+                    B.append(f"  const {T} {oname(v, zo, k)} = ({' && '.join(conds)}) ? {res[(v, k)]} : ({T})0;")
                 else:
-                    B.append(f"  const {T} o{v}_{k} = {res[(v, k)]};")
+                    B.append(f"  const {T} {oname(v, zo, k)} = {res[(v, k)]};")
         if need_gmy:
             idx = B.index(f"  const int row = {row_expr};")
             B.insert(idx + 1, f"  const int gmy = row - g.yorg + g.y0 + {mly}; const int memy = g.ny + {mly + mhy};   // row in the reference memory box")
         for (s, v) in st.store_targets:
             T = self.T(v)
             vt = VEC_TYPE.get((T, V))
-            P(f"{T}* __restrict__ po{s} = {self.outp(s, T)} + (ptrdiff_t)r0 * g.pitch + tc;   // advances one row per output row")
-            B.append(f"  {{ {T}* __restrict__ p = po{s}; po{s} += g.pitch;")
+            zo = splane(s, v)
+            ps = f"po{s}" if zo == 0 else f"po{s}z{zo}"
+            on = [oname(v, zo, k) for k in range(V)]
+            P(f"{T}* __restrict__ {ps} = {self.outp(s, T)} + (ptrdiff_t)r0 * g.pitch + tc" + (f" + (ptrdiff_t){zo} * g.plane" if zo else "") +
+              ";   // advances one row per output row")
+            B.append(f"  {{ {T}* __restrict__ p = {ps}; {ps} += g.pitch;" + (f" if ({zlive(zo)}) {{" if zo else ""))
             if vt:
-                mk = f"make_{vt}({', '.join(f'o{v}_{k}' for k in range(V))})"
+                mk = f"make_{vt}({', '.join(on)})"
                 if self.tuning.store_hint == "cs":      # streaming store (evict-first): the row is not read again before the next step
                     B.append(f"    if (li_all) {{ __stcs(reinterpret_cast<{vt}*>(p), {mk}); }}")
                 elif self.tuning.store_hint == "cg":
@@ -728,11 +742,11 @@ class StageEmitter:
                     B.append(f"    if (li_all) {{ *reinterpret_cast<{vt}*>(p) = {mk}; }}")
                 B.append("    else if (li_any) {")
                 for k in range(V):
-                    B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = o{v}_{k};")
+                    B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
                 B.append("    }")
             else:
                 for k in range(V):
-                    B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = o{v}_{k};")
+                    B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
             # fused ghost-cell writes for Cyclic axes: the wrap the reference evaluates with % on every
             # read (PlanTrans.hs:477-484) is materialised once per written cell
             B.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
@@ -740,14 +754,14 @@ class StageEmitter:
                 B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
                 B.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
                 B.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
-                B.append(f"        if (dc) p[{k} + dc] = o{v}_{k};")
-                B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
-                B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = o{v}_{k};")
-                B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = o{v}_{k};   // domain narrower than the ghost width")
-                B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = o{v}_{k};")
+                B.append(f"        if (dc) p[{k} + dc] = {on[k]};")
+                B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]};   // domain narrower than the ghost width")
+                B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = {on[k]};")
                 B.append("      }")
             B.append("    } }")
-            B.append("  }")
+            B.append("  }" + ("}" if zo else ""))
         def accumulate(v, rop, slot, names, ind):
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             chain = f"acc{slot}"
@@ -758,8 +772,13 @@ class StageEmitter:
             for k in range(V):
                 B.append(f"{ind}  if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{slot} = {cls}::op(acc{slot}, {names[k]});")
             B.append(f"{ind}}}")
-        for (v, rop, slot) in st.reduce_targets:
-            accumulate(v, rop, slot, [f"o{v}_{k}" for k in range(V)], "  ")
+        for n, (v, rop, slot) in enumerate(st.reduce_targets):
+            zo = rplane(n)
+            if zo:
+                B.append(f"  if ({zlive(zo)}) {{")
+            accumulate(v, rop, slot, [oname(v, zo, k) for k in range(V)], "    " if zo else "  ")
+            if zo:
+                B.append("  }")
         if st.carried:
             # the level-0 reduce of the NEXT call of this kernel, evaluated on the values just stored (schedule.find_carry)
             B.append("  {   // carried reduce: next call's level-0 stage becomes an 8-byte copy")
@@ -771,13 +790,23 @@ class StageEmitter:
         B.append("}")
         return B
 
+    def reduce_slots_once(self) -> List[Tuple[int, str, int]]:
+        """One (value, op, slot) per reduce slot of the stage (a rank-3 CTA that computes several planes accumulates
+        several values into the same slot)."""
+        seen, out = set(), []
+        for (v, rop, slot) in self.st.reduce_targets + self.st.carried:
+            if slot not in seen:
+                seen.add(slot)
+                out.append((v, rop, slot))
+        return out
+
     def emit_reduce_epilogue(self) -> List[str]:
         st = self.st
         L: List[str] = []
         if not (st.reduce_targets or st.carried):
             return L
         L.append("  // block reduce -> per-CTA partial -> the last CTA folds all partials (om_runtime.cuh)")
-        for t, (v, rop, slot) in enumerate(st.reduce_targets + st.carried):
+        for t, (v, rop, slot) in enumerate(self.reduce_slots_once()):
             T = self.T(v)
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
@@ -795,7 +824,7 @@ class StageEmitter:
         st = self.st
         sv = self.om.setup.static_values
         in_statics = sorted({i.static_idx for i in st.inputs.values()})
-        out_statics = [s for (s, _v) in st.store_targets]
+        out_statics = list(dict.fromkeys(s for (s, _v) in st.store_targets))
         args = ["*g"]
         for s in in_statics:
             args.append(f"(const {CPP_TYPE[sv[s].namee.type]}*)cur[{s}]")
@@ -815,7 +844,7 @@ class StageEmitter:
         L.append("  static bool attr_set[64] = {};   // function attributes are per device")
         L.append("  int dev = 0; cudaGetDevice(&dev);")
         L.append(f"  if (dev >= 64 || !attr_set[dev]) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; if (dev < 64) attr_set[dev] = true; }}")
-        L.append("  const int planes = g->own_z1 - g->own_z0;   // rank 3: one layer of CTAs per plane of axis 2 (1 otherwise)")
+        L.append(f"  const int planes = (g->own_z1 - g->own_z0 + {st.zplanes - 1}) / {st.zplanes};   // rank 3: one layer of CTAs per group of {st.zplanes} plane(s) of axis 2")
         L.append("  if (planes <= 0) return 0;")
         L.append(f"  OM_LAUNCH({self.name}_kernel, dim3(strips, chunks, planes), {self.NT}, {smem}, (cudaStream_t)stream, {', '.join(args)});")
         L.append("  OM_CUDA_CHECK_LAUNCH();")

@@ -57,13 +57,13 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
             stages.append(dict(
                 symbol=em.name, level=st.level, V=em.V, NT=em.NT, smem=em.smem_bytes(), w_out=em.W_OUT,
                 inputs=sorted({i.static_idx for i in st.inputs.values()}),
-                outputs=[s for (s, _v) in st.store_targets],
+                outputs=list(dict.fromkeys(s for (s, _v) in st.store_targets)), zplanes=st.zplanes,
                 reduces=[dict(op=rop, slot=slot, type=ks.ops[v].ctype,
                               # deferred: only stored, unchanged, into scalars that no kernel loads
                               deferred=(slot_to_vid[slot] not in consumed and slot_to_vid[slot] in direct_store and
                                         all(sx not in loaded_scalars for sx in direct_store[slot_to_vid[slot]])),
                               stored_to=direct_store.get(slot_to_vid[slot], []))
-                         for (v, rop, slot) in st.reduce_targets] +
+                         for (v, rop, slot) in {t[2]: t for t in reversed(st.reduce_targets)}.values()][::-1] +
                         # carried: the next call's level-0 reduce, produced by this stage (consumed on the device)
                         [dict(op=rop, slot=slot, type=ks.ops[v].ctype, deferred=False, stored_to=[], carried=True)
                          for (v, rop, slot) in st.carried],
@@ -73,7 +73,7 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
         kernels.append(dict(
             name=ks.name, stages=stages,
             scalars=(f"om_{om.name}_{ks.name}_scalars" if ks.scalar_stores else None),
-            array_stores=[s for (s, _v) in ks.array_stores],
+            array_stores=list(dict.fromkeys(s for (s, _v) in ks.array_stores)),
             scalar_stores=[s for (s, _v) in ks.scalar_stores],
             loaded_arrays=ks.loaded_arrays,
             # carry: {skip_stage, pairs [(reduce slot, carry slot)], arrays, scalars}: when the previous call on this
@@ -97,7 +97,7 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     schedules: List[KernelSchedule] = []
     slot = nstat
     for k in om.kernels:
-        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces)
+        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces, setup.tuning.planes_per_cta)
         slot += len(ks.reduce_slots) + ks.extra_slots
         schedules.append(ks)
     cu: List[str] = [

@@ -91,6 +91,9 @@ class Stage:
     out_level: int = 1                   # phase in which the OUT scope (stores / reduces) runs
     mat_candidates: List[dict] = field(default_factory=list)   # shifted values: {vid, op, cost, default, chosen}
     carried: List[Tuple[int, str, int]] = field(default_factory=list)   # (value id, op, slot): next call's level-0 reduces
+    zplanes: int = 1                                                    # rank 3: planes of axis 2 one CTA computes
+    store_plane: Dict[Tuple[int, int], int] = field(default_factory=dict)   # (static, value id) -> plane offset inside the CTA's group
+    reduce_plane: List[int] = field(default_factory=list)                   # plane offset of every reduce_targets entry
 
 
 @dataclass
@@ -173,7 +176,7 @@ def fold_ops(g: Graph, dim: int, normalize: bool = True, pull_shifts: bool = Fal
     return ops, stores
 
 
-def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int, Op], List[Tuple[int, int]]]:
+def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]], zplanes: int = 1):
     """Rank-3 machines: turn the op DAG into a rank-2 DAG per plane of axis 2.
 
     A CTA of a rank-3 machine works inside one plane z of axis 2 (blockIdx.z), streaming along axis 1 exactly like a
@@ -183,7 +186,12 @@ def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int
     axis 1) part only.  This is the reference's own evaluation rule (every Delayed value is recomputed at the cursor
     it is requested at, PlanTrans.hs:527-544) applied to axis 2; along axes 0 and 1 the shared-memory rings of the
     rank-2 schedule still remove the recomputation.  Neighbouring planes are re-read by the CTAs of the planes next to
-    them, i.e. from L2."""
+    them, i.e. from L2.
+
+    With `zplanes` = Z > 1 a CTA computes Z consecutive planes: every store exists once per plane offset zo in [0, Z)
+    and a Reduce folds its argument at all Z offsets, so the rows of Z + 2r planes are staged for Z planes of output
+    instead of 1 + 2r for one (the virtual inputs of neighbouring offsets coincide and are merged).
+    Returns (ops, [(static, value, zo)], {value: zo})."""
     def zc(a: int, cz: int) -> int:      # position-independent values exist once
         o = ops[a]
         if o.realm == SCALAR or o.kind in ("Imm", "Broadcast", "LoadSize") or (o.kind == "LoadIndex" and o.inst.arg != 2):
@@ -191,7 +199,10 @@ def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int
         return cz
     need: Dict[int, Set[int]] = {v: set() for v in ops}
     for (_s, v) in stores:
-        need[v].add(0)
+        if ops[v].realm == ARRAY:
+            need[v].update(zc(v, zo) for zo in range(zplanes))
+        else:
+            need[v].add(0)
     for v in sorted(ops):
         if ops[v].kind == "Reduce":
             need[v].add(0)
@@ -201,7 +212,10 @@ def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int
             if o.kind == "Shift":
                 a = o.args[0]
                 need[a].add(zc(a, cz - tuple(o.inst.arg)[2]))
-            elif o.kind in ("Reduce", "Broadcast") or o.realm == SCALAR:
+            elif o.kind == "Reduce":
+                for a in o.args:
+                    need[a].update(zc(a, zo) for zo in range(zplanes))
+            elif o.kind == "Broadcast" or o.realm == SCALAR:
                 for a in o.args:
                     need[a].add(0)
             else:
@@ -228,7 +242,9 @@ def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int
                         m[(v, cz)] = src
                         continue
                 inst, args = Inst("Shift", (vec[0], vec[1])), [src]
-            elif kind in ("Reduce", "Broadcast") or o.realm == SCALAR:
+            elif kind == "Reduce":       # the argument at every plane offset of the CTA's group, in offset order
+                args = [m[(a, zc(a, zo))] for a in o.args for zo in range(zplanes)]
+            elif kind == "Broadcast" or o.realm == SCALAR:
                 args = [m[(a, 0)] for a in o.args]
             else:
                 args = [m[(a, zc(a, cz))] for a in o.args]
@@ -241,7 +257,13 @@ def lower_z(ops: Dict[int, Op], stores: List[Tuple[int, int]]) -> Tuple[Dict[int
                 out[nid] = Op(nid, kind, inst, args, o.realm, o.ctype, o.valid, zoff)
                 table[key] = nid
             m[(v, cz)] = table[key]
-    return out, [(s_, m[(v, 0)]) for (s_, v) in stores]
+    stores_z = []
+    for (s_, v) in stores:
+        if ops[v].realm == ARRAY:
+            stores_z += [(s_, m[(v, zc(v, zo))], zo) for zo in range(zplanes)]
+        else:
+            stores_z.append((s_, m[(v, 0)], 0))
+    return out, stores_z
 
 
 def _cost(op: Op) -> int:
@@ -516,12 +538,17 @@ def find_carry(ops: Dict[int, Op], rl: Dict[int, int], reduce_slots: Dict[int, i
 
 
 def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=(),
-                    carry_reduces: bool = True) -> KernelSchedule:
+                    carry_reduces: bool = True, zplanes: int = 1) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
+    plane_of: Dict[Tuple[int, int], int] = {}
     if dim == 3:
-        ops, stores = lower_z(ops, stores)
+        ops, stores_z = lower_z(ops, stores, zplanes)
+        stores = [(s_, v) for (s_, v, _zo) in stores_z]
+        plane_of = {(s_, v): zo for (s_, v, zo) in stores_z}
+    else:
+        zplanes = 1
     # reduce levels
     rl: Dict[int, int] = {}
     for v in sorted(ops):
@@ -538,7 +565,7 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
                     {rl[ops[v].args[0]] for v in reduce_slots})
     stages: List[Stage] = []
     loaded: Set[int] = set()
-    found = find_carry(ops, rl, reduce_slots, array_stores, scalar_stores, levels) if carry_reduces else None
+    found = find_carry(ops, rl, reduce_slots, array_stores, scalar_stores, levels) if (carry_reduces and zplanes == 1) else None
     carry = None
     if found:
         ops.update(found["new_ops"])
@@ -548,8 +575,11 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
     for L in levels:
         st = Stage(kernel=kernel.name, level=L)
         st.store_targets = [(s, v) for (s, v) in array_stores if rl[v] == L]
-        st.reduce_targets = [(ops[v].args[0], ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
-                             if rl[ops[v].args[0]] == L]
+        st.reduce_targets = [(a, ops[v].inst.arg, reduce_slots[v]) for v in sorted(reduce_slots)
+                             if rl[ops[v].args[0]] == L for a in ops[v].args]
+        st.reduce_plane = [zo for v in sorted(reduce_slots) if rl[ops[v].args[0]] == L for zo in range(len(ops[v].args))]
+        st.zplanes = zplanes
+        st.store_plane = {(s_, v): plane_of.get((s_, v), 0) for (s_, v) in st.store_targets}
         roots = [v for (_s, v) in st.store_targets] + [v for (v, _o, _k) in st.reduce_targets]
         if found and L == found["level"]:
             st.carried = [(c, rop, carry["pairs"][n][1]) for n, (_r, c, rop) in enumerate(found["roots"])]

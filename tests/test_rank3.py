@@ -54,3 +54,23 @@ def test_life3d_bit_exact(bnd, size):
 def test_diffusion3d_bit_identical(bnd):
     setup = Setup(local_size=(70, 12, 7), boundary=bnd)
     run_both3(diffusion3d_om, setup, ["init", "proceed", "proceed"], f"diff3d_{''.join(b[0] for b in bnd)}", {})
+
+
+@pytest.mark.parametrize("zplanes,size", [(2, (37, 11, 6)), (2, (20, 9, 5)), (4, (33, 7, 10)), (3, (16, 5, 1))])
+def test_life3d_several_planes_per_cta(zplanes, size):
+    """Tuning.planes_per_cta: a CTA computes Z consecutive planes (Z + 2 planes staged for Z planes of output); the last
+    group may be incomplete (6 = 3 x 2, 5 = 2 x 2 + 1, 10 = 2 x 4 + 2, 1 < 3)."""
+    setup = Setup(local_size=size, boundary=(CYCLIC, CYCLIC, CYCLIC))
+    setup.tuning.planes_per_cta = zplanes
+    fill = {"cell": (np.random.default_rng(12).random(mem_shape3(setup, life3d_om)) < 0.3).astype(np.int32)}
+    desc, so = build_emulated(setup, life3d_om(), tag=f"life3d_z{zplanes}")
+    assert desc["kernels"][0]["stages"][0]["zplanes"] == zplanes
+    run_both3(life3d_om, setup, ["proceed"] * 3, f"life3d_z{zplanes}", fill)
+
+
+@pytest.mark.parametrize("bnd", [(OPEN, OPEN, OPEN), (CYCLIC, OPEN, CYCLIC)])
+def test_diffusion3d_two_planes_per_cta(bnd):
+    """Open axis 2 (valid masks per plane offset), a Max reduce over both planes of a group, loadIndex(2) per plane."""
+    setup = Setup(local_size=(70, 12, 7), boundary=bnd)
+    setup.tuning.planes_per_cta = 2
+    run_both3(diffusion3d_om, setup, ["init", "proceed", "proceed"], f"diff3d_z2_{''.join(b[0] for b in bnd)}", {})
