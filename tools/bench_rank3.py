@@ -9,7 +9,7 @@ import torch  # noqa: E402
 
 from paraiso_b200.build import build_machine  # noqa: E402
 from paraiso_b200.examples.rank3 import life3d_om  # noqa: E402
-from paraiso_b200.generator.native import Setup  # noqa: E402
+from paraiso_b200.generator.native import Setup, Tuning  # noqa: E402
 from paraiso_b200.runtime import Machine  # noqa: E402
 from paraiso_b200.tuning import measure  # noqa: E402
 
@@ -17,6 +17,7 @@ def heat(n, z):
     from paraiso_b200.examples.rank3 import heat3d_om
     size = (n, n, n)
     setup = Setup(local_size=size, boundary=("Cyclic", "Cyclic", "Cyclic"))
+    setup.tuning = Tuning.from_env(setup.tuning)       # OM_* overrides (sweeps)
     setup.tuning.planes_per_cta = z
     desc, so = build_machine(setup, heat3d_om(), tag=f"Heat3_bench_z{z}")
     m = Machine(desc, so, size=size)
