@@ -70,5 +70,8 @@ def life_om(variant: str = "master") -> OM:
 
 def life_setup(variant: str = "master", size=None) -> Setup:
     if variant == "master":  # Generator.hs:39-44
-        return Setup(local_size=size or (80, 48), boundary=(CYCLIC, CYCLIC), directory="./dist/")
-    return Setup(local_size=size or (128, 128), boundary=(OPEN, OPEN), directory="./dist/")  # LifeMain.hs:121-125
+        s = Setup(local_size=size or (80, 48), boundary=(CYCLIC, CYCLIC), directory="./dist/")
+    else:
+        s = Setup(local_size=size or (128, 128), boundary=(OPEN, OPEN), directory="./dist/")  # LifeMain.hs:121-125
+    s.tuning.prefetch_rows = 3     # three rows in flight per CTA: the winner of every sweep in profiles/r1_life_sweep.txt
+    return s

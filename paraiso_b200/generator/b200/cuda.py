@@ -488,6 +488,10 @@ class StageEmitter:
                 B.append(f"if (it >= {self.PF}) om_mbar_wait(&mbar[bar_w], bar_wp);")
                 return
             B.append("// stage the next input rows (LDGSTS); the apron rows around every array make bounds checks unnecessary")
+            # (rows beyond the chunk's last needed row are not fetched: without the test every chunk would read
+            #  prefetch_rows rows it never uses — 6 % more DRAM reads for 32-row chunks)
+            jx = "j" if self.window_u is None else f"j + {self.window_u}"
+            B.append(f"if ({jx} + {self.PF} < r1) {{")
             for i in self.ring_inputs:
                 v = i.vid
                 T = self.T(v)
@@ -502,6 +506,7 @@ class StageEmitter:
                 if self.PR:
                     B.append(f"if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
                 B.append(f"src{v} += g.pitch;")
+            B.append("}")
             B.append("om_cp_async_commit();")
             B.append(f"om_cp_async_wait<{self.PF}>();")
 
