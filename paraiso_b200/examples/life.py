@@ -73,5 +73,7 @@ def life_setup(variant: str = "master", size=None) -> Setup:
         s = Setup(local_size=size or (80, 48), boundary=(CYCLIC, CYCLIC), directory="./dist/")
     else:
         s = Setup(local_size=size or (128, 128), boundary=(OPEN, OPEN), directory="./dist/")  # LifeMain.hs:121-125
-    s.tuning.prefetch_rows = 3     # three rows in flight per CTA: the winner of every sweep in profiles/r1_life_sweep.txt
+    # winners of the sweeps in profiles/r1_life_sweep.txt: three rows in flight per CTA, 24-row chunks
+    s.tuning.prefetch_rows = 3
+    s.tuning.chunk_rows_light = 24
     return s
