@@ -490,8 +490,10 @@ class StageEmitter:
             B.append("// stage the next input rows (LDGSTS); the apron rows around every array make bounds checks unnecessary")
             # (rows beyond the chunk's last needed row are not fetched: without the test every chunk would read
             #  prefetch_rows rows it never uses — 6 % more DRAM reads for 32-row chunks)
+            # (short chunks only, i.e. row-window stages: in the heavy stages' one-wave chunks of hundreds of rows the test
+            #  saves nothing and costs the flux kernel 4 %)
             jx = "j" if self.window_u is None else f"j + {self.window_u}"
-            B.append(f"if ({jx} + {self.PF} < r1) {{")
+            B.append(f"if ({jx} + {self.PF} < r1) {{" if self.window else "{")
             for i in self.ring_inputs:
                 v = i.vid
                 T = self.T(v)
