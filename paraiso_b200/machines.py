@@ -17,11 +17,8 @@ def build_life(fmad: bool = False, verbose: bool = False):
 def build_hydro(real: str = "Double", fmad: bool = False, verbose: bool = False, fast: bool = False):
     """examples/Hydro/HydroMain.hs (Open, Real = Double upstream).  `fast` = Setup.fast_math (implies FMA)."""
     setup = hydro_setup(fast=fast)
-    if fast and not setup.tuning.mat_flip:
-        # winner of tuning.local_search on the B200 (profiles/r1_hydro_search_fast.jsonl): the boundary-conditioned
-        # pressure (value 362, a select over a load) is recomputed at its cursors instead of kept in a ring, +4 %.
-        # The IEEE build keeps the threshold rule (profiles/r1_hydro_search_exact.jsonl: no flip gains).
-        setup.tuning.mat_flip = (("proceed", 362),)
+    # (per-node genes: tuning.local_search finds no flip that pays for either build at their present CTA shapes —
+    #  profiles/r1_hydro_search_*.jsonl; with two 256-thread CTAs per SM the fast build gained 4 % from flipping value 362)
     return build_machine(setup, hydro_om("master", real=real), tag=f"Hydro_OO_{real}{'_fast' if fast else ''}",
                          fmad=fmad or fast, verbose=verbose)
 

@@ -23,6 +23,11 @@ if __name__ == "__main__":
         if "ms" in r:
             r["Gcell_per_s"] = size[0] * size[1] / r["ms"] / 1e6
         print(json.dumps(r), flush=True)
-    best = local_search(lambda: hydro_setup(fast=fast), lambda: hydro_om("master"), size, prepare=prepare, fmad=fast,
+    def mk():
+        from paraiso_b200.generator.native import Tuning
+        s = hydro_setup(fast=fast)
+        s.tuning = Tuning.from_env(s.tuning)        # OM_* overrides of the start individual's knobs
+        return s
+    best = local_search(mk, lambda: hydro_om("master"), size, prepare=prepare, fmad=fast,
                         steps=10, passes=2, budget_s=budget, log=log)
     print("BEST", json.dumps(dict(mat_flip=best["mat_flip"], ms=best["ms"])), flush=True)
