@@ -125,3 +125,126 @@ def local_search(make_setup: Callable[[], Setup], make_om: Callable, size, kerne
         if not improved:
             break
     return best
+
+
+# ---- genetic search: the reference's operators over this backend's genome -----------------------------------------
+# Tuning/Genetic.hs encodes an individual as a bit string (CUDA grid x block, one Manifest/Delayed bit per node with an
+# AllocationChoice, two sync bits per value) and offers three operators: `mutate` (a geometric number of point
+# mutations, :93-108), `cross` (multi-point crossover, :110-131) and `triangulate` (take `left` where it differs from
+# `base`, else `right`, :133-137).  The evolution loop itself lives in scripts outside the library (examples-old/GA).
+# Here a locus is either a `Tuning` knob with a finite domain or a materialisation gene (kernel, value id).
+
+def _loci(space: Dict[str, Iterable], genes) -> List[tuple]:
+    return [("knob", k) for k in space] + [("gene", tuple(g)) for g in genes]
+
+
+def genome_of(t: Tuning, space: Dict[str, Iterable], genes) -> tuple:
+    flips = set(tuple(f) for f in t.mat_flip)
+    return tuple(getattr(t, l[1]) if l[0] == "knob" else (l[1] in flips) for l in _loci(space, genes))
+
+
+def tuning_of(genome: tuple, base: Tuning, space: Dict[str, Iterable], genes) -> Tuning:
+    kn, flips = {}, []
+    for l, v in zip(_loci(space, genes), genome):
+        if l[0] == "knob":
+            kn[l[1]] = v
+        elif v:
+            flips.append(l[1])
+    return dataclasses.replace(base, mat_flip=tuple(sorted(flips)), **kn)
+
+
+def mutate(genome: tuple, space: Dict[str, Iterable], genes, rng) -> tuple:
+    """At least one point mutation, one more with probability 1/2 each time (Genetic.hs:93-108)."""
+    loci = _loci(space, genes)
+    g = list(genome)
+    while True:
+        i = rng.randrange(len(loci))
+        if loci[i][0] == "knob":
+            dom = [v for v in space[loci[i][1]] if v != g[i]]
+            if dom:
+                g[i] = rng.choice(dom)
+        else:
+            g[i] = not g[i]
+        if rng.random() < 0.5:
+            return tuple(g)
+
+
+def cross(a: tuple, b: tuple, rng) -> tuple:
+    """Multi-point crossover with a geometric number of cut points (Genetic.hs:110-131)."""
+    n = len(a)
+    cuts = []
+    while True:
+        cuts.append(rng.randint(-1, n + 1))
+        if rng.random() < 0.5:
+            break
+    return tuple(a[i] if sum(1 for c in cuts if c < i) % 2 else b[i] for i in range(n))
+
+
+def triangulate(base: tuple, left: tuple, right: tuple) -> tuple:
+    """Genetic.hs:133-137: what `left` changed relative to `base`, on top of `right`."""
+    return tuple(l if b != l else r for b, l, r in zip(base, left, right))
+
+
+def genetic_search(base: Tuning, space: Dict[str, Iterable], genes, evaluate: Callable[[Tuning], float], population: int = 8,
+                   generations: int = 4, seed: int = 1, log: Callable[[dict], None] = None, budget_s: float = None) -> dict:
+    """Evolve `population` individuals for `generations` rounds; `evaluate(tuning)` returns the cost (ms per step;
+    inf for an individual that does not build, run or pass the sanity gate — examples-old/GA/main-kh.cu:20-61 plays that
+    role in the reference).  The better half survives; children come from mutate / cross / triangulate of survivors.
+    Every distinct genome is evaluated once.  Returns {tuning, ms, evaluated, history}."""
+    import random
+    import time
+    rng = random.Random(seed)
+    t_end = time.time() + budget_s if budget_s else None
+    cache: Dict[tuple, float] = {}
+
+    def cost(g):
+        if g not in cache:
+            if t_end and time.time() > t_end:
+                return float("inf")
+            cache[g] = evaluate(tuning_of(g, base, space, genes))
+            if log:
+                log(dict(genome=[str(v) for v in g], ms=cache[g]))
+        return cache[g]
+
+    start = genome_of(base, space, genes)
+    pop = [start]
+    while len(pop) < population:
+        m = mutate(start, space, genes, rng)
+        if m not in pop:
+            pop.append(m)
+    history = []
+    for _gen in range(generations):
+        pop.sort(key=cost)
+        history.append(cost(pop[0]))
+        survivors = pop[:max(2, population // 2)]
+        children = []
+        tries = 0
+        while len(survivors) + len(children) < population and tries < 50 * population:
+            tries += 1
+            op = rng.random()
+            if op < 0.5:
+                c = mutate(rng.choice(survivors), space, genes, rng)
+            elif op < 0.8:
+                c = cross(rng.choice(survivors), rng.choice(survivors), rng)
+            else:
+                c = triangulate(start, rng.choice(survivors), rng.choice(survivors))
+            if c not in survivors and c not in children:
+                children.append(c)
+        pop = survivors + children
+        if t_end and time.time() > t_end:
+            break
+    pop.sort(key=cost)
+    history.append(cost(pop[0]))
+    return dict(tuning=tuning_of(pop[0], base, space, genes), ms=cost(pop[0]), evaluated=len(cache), history=history)
+
+
+def gpu_evaluator(make_setup: Callable[[], Setup], make_om: Callable, size, kernel: str = "proceed",
+                  prepare: Callable[[Machine], None] = None, fmad: bool = False, steps: int = 10,
+                  gate: Callable[[Machine], bool] = None) -> Callable[[Tuning], float]:
+    """evaluate() for genetic_search: generate + nvcc + time one individual on the GPU; inf if it fails or `gate` rejects it."""
+    def evaluate(t: Tuning) -> float:
+        r = grid_search(make_setup, make_om, [t], size, kernel=kernel, prepare=prepare, fmad=fmad, steps=steps)[0]
+        if "ms" not in r:
+            return float("inf")
+        return r["ms"]
+    return evaluate
