@@ -265,7 +265,7 @@ def main():
                              "algorithmic_bytes_per_cell": alg_bytes, "kernel_ms": kms},
                 "e2e": {"value": e2e_value, "unit": "Gcell/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "gpu_launches": launches, "clocks": clocks}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg runs at N = 1 only (ranks of a multi-GPU job do not wait for it)
             sample = (4096, 4096) if args.workload == "life" else (1024, 1024)
             csteps = 5 if args.workload == "life" else 3
             v, _ = time_cpu("life" if args.workload == "life" else "hydro", sample, csteps, 1)

@@ -30,7 +30,6 @@ from .annotation import CYCLIC
 TORCH_TYPE = {"Int": torch.int32, "Float": torch.float32, "Double": torch.float64, "Bool": torch.bool,
               "Integer": torch.int64}
 NP_TYPE = {"Int": np.int32, "Float": np.float32, "Double": np.float64, "Bool": np.bool_, "Integer": np.int64}
-SM_COUNT = 148
 APRON = 16   # = APRON_ROWS of generator/b200/cuda.py
 
 
@@ -319,9 +318,7 @@ class Machine:
         import torch.distributed as dist
         op = {"Sum": dist.ReduceOp.SUM, "Min": dist.ReduceOp.MIN, "Max": dist.ReduceOp.MAX}[r["op"]]
         view = self.sc[r["slot"]:r["slot"] + 1].view(TORCH_TYPE[r["type"]])[:1]
-        dist.all_reduce(view, op=op, group=self.group)
-        if view.element_size() < 8:   # keep the unused half of the slot zero
-            pass
+        dist.all_reduce(view, op=op, group=self.group)   # 4-byte types reduce the low half of the slot; the rest stays zero
 
     def _exchange_rows(self, a: torch.Tensor):
         """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too).  Rank-3 machines are cut
