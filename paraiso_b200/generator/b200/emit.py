@@ -97,7 +97,8 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     schedules: List[KernelSchedule] = []
     slot = nstat
     for k in om.kernels:
-        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces, setup.tuning.planes_per_cta)
+        ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces, setup.tuning.planes_per_cta,
+                             setup.tuning.sink_selects)
         slot += len(ks.reduce_slots) + ks.extra_slots
         schedules.append(ks)
     cu: List[str] = [

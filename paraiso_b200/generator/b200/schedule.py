@@ -107,6 +107,7 @@ class KernelSchedule:
     loaded_arrays: List[int]                      # static idx of arrays read by any stage
     carry: Optional[dict] = None                  # reduce carried to the next call (find_carry)
     extra_slots: int = 0                          # scalar slots used beyond the reduce slots
+    sink_stats: Optional[dict] = None             # selectsink.sink_selects report (weighted DAG size before / after)
 
 
 COMMUTATIVE = {"Add", "Mul", "And", "Or", "EQ", "NE"}
@@ -538,10 +539,14 @@ def find_carry(ops: Dict[int, Op], rl: Dict[int, int], reduce_slots: Dict[int, i
 
 
 def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=(),
-                    carry_reduces: bool = True, zplanes: int = 1) -> KernelSchedule:
+                    carry_reduces: bool = True, zplanes: int = 1, sink_selects: bool = True) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
+    sink_stats = None
+    if sink_selects:
+        from .selectsink import sink_selects as _sink
+        ops, stores, sink_stats = _sink(ops, stores)
     plane_of: Dict[Tuple[int, int], int] = {}
     if dim == 3:
         ops, stores_z = lower_z(ops, stores, zplanes)
@@ -591,4 +596,4 @@ def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int =
         stages.append(st)
     return KernelSchedule(name=kernel.name, ops=ops, stages=stages, scalar_stores=scalar_stores,
                           array_stores=array_stores, reduce_slots=reduce_slots, loaded_arrays=sorted(loaded),
-                          carry=carry, extra_slots=len(carry["pairs"]) if carry else 0)
+                          carry=carry, extra_slots=len(carry["pairs"]) if carry else 0, sink_stats=sink_stats)
