@@ -539,11 +539,15 @@ def find_carry(ops: Dict[int, Op], rl: Dict[int, int], reduce_slots: Dict[int, i
 
 
 def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=(),
-                    carry_reduces: bool = True, zplanes: int = 1, sink_selects: bool = True) -> KernelSchedule:
+                    carry_reduces: bool = True, zplanes: int = 1, sink_selects: bool = True,
+                    fast_algebra: bool = False) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
     ops, stores = fold_ops(g, dim)
     sink_stats = None
+    if fast_algebra:
+        from .selectsink import simplify_fast
+        ops, stores, _removed = simplify_fast(ops, stores)
     if sink_selects:
         from .selectsink import sink_selects as _sink
         ops, stores, sink_stats = _sink(ops, stores)

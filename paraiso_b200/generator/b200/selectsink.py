@@ -336,3 +336,83 @@ def sink_selects(ops: Dict[int, "Op"], stores: List[Tuple[int, int]]):
         return ops, stores, stats
     new_ops, new_stores = sk.result(stores)
     return new_ops, new_stores, stats
+
+
+def simplify_fast(ops: Dict[int, "Op"], stores: List[Tuple[int, int]]):
+    """Algebraic clean-up for `Setup.fast_math` builds only (results within rounding of the reference, not bit-identical).
+
+    The Builder's `sum` / `contract` fold from an explicit zero and dot products with unit vectors multiply by literal
+    0 and 1 (visible in the reference's own output, Hydro.cpp:204-205), and the HLLC star state divides a product by
+    one of its factors (`mome / dens` with `mome = dens * v`, HydroMain.hs:243-248):
+        x * 0 -> 0      x * 1 -> x      x + 0 -> x      x - 0 -> x      x / 1 -> x      select c a a -> a
+        (a * b) / b -> a                                                   (one rounding instead of two)
+    The first group is exact for finite x up to the sign of a zero; the last differs from the reference by <= 1 ulp.
+    Ids are kept (every replacement is an earlier node), duplicates created by the rewrites are merged.
+    Returns (ops, stores, number of nodes removed)."""
+    from .schedule import Op
+    from ...om.graph import imm_value
+    protected = set(v for (_s, v) in stores)
+    for v in ops:
+        if ops[v].kind in ("Reduce", "Broadcast"):
+            protected.update(ops[v].args)
+    canon: Dict[int, int] = {}
+    out: Dict[int, Op] = {}
+    table: Dict[tuple, int] = {}
+
+    def const(v: int):
+        o = out[v]
+        if o.kind == "Imm" and o.ctype in ("Double", "Float"):
+            return float(imm_value(o.inst.arg, o.ctype))
+        return None
+
+    for v in sorted(ops):
+        o = ops[v]
+        args = [canon[a] for a in o.args]
+        r = None
+        if o.kind == "Arith" and o.ctype in ("Double", "Float") and v not in protected:
+            t = o.inst.arg
+            c = [const(a) for a in args]
+            if t == "Mul":
+                if 0.0 in c:
+                    r = args[c.index(0.0)]
+                elif c[0] == 1.0:
+                    r = args[1]
+                elif c[1] == 1.0:
+                    r = args[0]
+            elif t == "Add":
+                if c[0] == 0.0:
+                    r = args[1]
+                elif c[1] == 0.0:
+                    r = args[0]
+            elif t == "Sub" and c[1] == 0.0:
+                r = args[0]
+            elif t == "Div":
+                num = out[args[0]]
+                if c[1] == 1.0:
+                    r = args[0]
+                elif num.kind == "Arith" and num.inst.arg == "Mul" and args[1] in num.args and num.args[0] != num.args[1]:
+                    r = num.args[1 - num.args.index(args[1])]
+            elif t == "Select" and args[1] == args[2]:
+                r = args[1]
+            if r is not None and (out[r].ctype != o.ctype or out[r].realm != o.realm):
+                r = None
+        if r is None:
+            if o.kind == "Arith" and o.inst.arg in COMMUTATIVE and len(args) == 2:
+                args = sorted(args)
+            key = _Sinker._key(o.kind, o.inst, args, o.realm, o.ctype, o.zoff)
+            if o.kind in ("Arith", "Shift") and key in table and v not in protected:
+                r = table[key]
+            else:
+                table.setdefault(key, v)
+                out[v] = Op(v, o.kind, o.inst, args, o.realm, o.ctype, o.valid, o.zoff)
+                r = v
+        canon[v] = r
+    # drop what is no longer reachable
+    live, stack = set(), [canon[v] for (_s, v) in stores] + [v for v in out if out[v].kind == "Reduce"]
+    while stack:
+        v = stack.pop()
+        if v not in live:
+            live.add(v)
+            stack.extend(out[v].args)
+    res = {v: out[v] for v in sorted(live)}
+    return res, [(s_, canon[v]) for (s_, v) in stores], len(ops) - len(res)

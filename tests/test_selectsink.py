@@ -94,3 +94,23 @@ def test_four_way_select_is_sunk_and_stays_bit_identical():
     shp = mem_shape(setup, _riemann_like_om)
     fill = {"q": rng.uniform(0.5, 2.0, shp), "u": rng.uniform(-2.0, 2.0, shp)}   # all four branches occur
     run_both(_riemann_like_om, setup, ["k"], "gen_riemann", fill)
+
+
+def test_fast_algebra_removes_zero_and_unit_terms_only_in_fast_builds():
+    """selectsink.simplify_fast: x*0, x+0, x*1, (a*b)/b -> a.  Ids are kept, store targets are never replaced, and the
+    exact build does not run the pass (schedule_kernel(fast_algebra=False) is the default)."""
+    from paraiso_b200.generator.b200.schedule import schedule_kernel
+    from paraiso_b200.generator.b200.selectsink import simplify_fast
+    ops, stores = _proceed_dag(hydro_setup(fast=True), hydro_om("master"))
+    new_ops, new_stores, removed = simplify_fast(ops, stores)
+    assert removed >= 60 and set(new_ops) <= set(ops)
+    assert [v for (_s, v) in new_stores] == [v for (_s, v) in stores]
+    h0, h1 = _hist(ops), _hist(new_ops)
+    assert h1["Mul"] <= h0["Mul"] - 24 and h1["Add"] <= h0["Add"] - 24 and h1["Div"] <= h0["Div"] - 12
+    for v, o in new_ops.items():
+        assert all(a in new_ops and a < v for a in o.args)
+    plan = translate(hydro_setup(), hydro_om("master"))
+    k = [k for k in plan.om.kernels if k.name == "proceed"][0]
+    exact = schedule_kernel(plan.om, k, 11)
+    fast = schedule_kernel(plan.om, k, 11, fast_algebra=True)
+    assert len(fast.ops) < len(exact.ops)
