@@ -1,0 +1,213 @@
+// om_runtime.cuh — device-side runtime shared by every generated B200 kernel file.
+//
+// Plays the role of the reference's embedded helper library (om_reduce_* / om_broadcast,
+// Language/Paraiso/Generator/PlanTrans.hs:719-720, readable form Generator/draft.cpp:4-39):
+// the serial / Thrust reductions become an in-kernel warp-shuffle + block reduction whose
+// per-CTA partials are folded by the last CTA to finish, and results stay in device memory.
+//
+// Written for sm_100a only.
+#pragma once
+#ifndef OM_EMULATED_INTRINSICS   // tests/emu/cuda_emu.h replaces the CUDA intrinsics to run kernels on host threads
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+#include <stddef.h>
+
+// Geometry of one rank's slab.  Arrays are stored row-major with axis 0 fastest
+// (PlanTrans.hs:449-454) but padded: `pitch` elements per row, interior cell (0, y0) at
+// device (row yorg, column xorg); ghost / margin cells surround the interior.
+struct OmGeom {
+  int nx, ny;                    // global interior size along axis 0 / axis 1
+  int pitch, rows;               // elements per row, local rows (ghost rows included)
+  int xorg, yorg;                // device column / row of the local interior origin
+  int y0;                        // global axis-1 index of local interior row 0
+  int nyl;                       // local interior rows
+  int gx_lo, gx_hi, gy_lo, gy_hi;// ghost widths actually allocated around the interior
+  int cyc_x, cyc_y;              // Cyclic boundary per axis (Annotation/Boundary.hs:35-38)
+  int wrap_y_local;              // cyclic axis 1 and this rank holds the whole axis: write ghost rows itself
+  int own_r0, own_r1;            // local rows of the reference memory box this rank owns (writes)
+  int chunk_rows;                // rows per CTA along axis 1
+  int red_accumulate;            // 1: fold this launch's reduce results into the slots instead of overwriting them
+                                 //    (a stage launched in several row ranges, e.g. boundary rows first, then the interior)
+  // rank-3 machines (1 / 0 / 0 / 0 / 0 / 0 / 0 / 1 / 0 / 1 otherwise): planes of `rows * pitch` elements stacked along axis 2
+  int nz, plane;                 // interior size along axis 2, elements per plane
+  int zorg, gz_lo, gz_hi, cyc_z; // device plane of interior plane 0, ghost planes, Cyclic axis 2
+  int own_z0, own_z1;            // device planes this launch computes (grid z)
+  int z0, nzl;                   // rank 3 with several ranks: the slab is cut along axis 2; global index of local plane 0, local planes
+};
+
+// Scalars (static Scalar-realm variables and reduce results) live in 8-byte device slots.
+typedef unsigned long long om_slot_t;
+
+template <class T> __device__ __forceinline__ T om_slot_load(const om_slot_t* sc, int i) {
+  return *reinterpret_cast<const T*>(sc + i);
+}
+template <class T> __device__ __forceinline__ void om_slot_store(om_slot_t* sc, int i, T v) {
+  om_slot_t z = 0;
+  *reinterpret_cast<T*>(&z) = v;
+  sc[i] = z;
+}
+
+// ---- async global->shared row staging (LDGSTS; zero-fill when src_bytes == 0) -------------
+#ifndef OM_EMULATED_INTRINSICS
+#define OM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define OM_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+__device__ __forceinline__ void om_cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void om_cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void om_cp_async4(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+template <int BYTES> __device__ __forceinline__ void om_cp_async(void* smem, const void* gmem, int src_bytes) {
+  static_assert(BYTES == 16 || BYTES == 8 || BYTES == 4, "cp.async moves 4, 8 or 16 bytes");
+  if (BYTES == 16) om_cp_async16(smem, gmem, src_bytes);
+  else if (BYTES == 8) om_cp_async8(smem, gmem, src_bytes);
+  else om_cp_async4(smem, gmem, src_bytes);
+}
+__device__ __forceinline__ void om_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void om_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// ---- TMA bulk row staging (cp.async.bulk -> UBLKCP) completing on an mbarrier -----------------------------------
+__device__ __forceinline__ void om_mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;\n" ::"r"(count), "r"(a) : "memory");
+}
+__device__ __forceinline__ void om_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void om_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;\n" ::"r"(bytes), "r"(a) : "memory");
+}
+// one contiguous row segment, global -> shared, by the TMA engine; src, dst and bytes are multiples of 16
+__device__ __forceinline__ void om_bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void om_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar), done;
+  do {   // try_wait suspends the thread in hardware up to a time limit; loop until the phase completes
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+#endif  // OM_EMULATED_INTRINSICS
+
+// ---- reductions (OM/Reduce.hs:9: Max | Min | Sum) ----------------------------------------------
+struct OmSum { template <class T> __device__ __forceinline__ static T op(T a, T b) { return a + b; } };
+struct OmMin { template <class T> __device__ __forceinline__ static T op(T a, T b) { return (b < a) ? b : a; } };  // std::min(a,b)
+struct OmMax { template <class T> __device__ __forceinline__ static T op(T a, T b) { return (a < b) ? b : a; } };  // std::max(a,b)
+
+template <class T> __device__ __forceinline__ T om_shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+template <class OP, class T> __device__ __forceinline__ T om_warp_reduce(T v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = OP::op(v, om_shfl_down(v, d));
+  return v;
+}
+
+// Block reduce + cross-CTA finalisation.  `scratch` layout: [0] arrival counter (u32),
+// partials for reduce target t at scratch_partials + t * max_blocks.
+// Returns true on the single thread (thread 0 of the last CTA) that holds the final value.
+template <class OP, class T, int NT>
+__device__ __forceinline__ bool om_block_reduce_finalize(T v, T identity, T* partials, unsigned* counter, T* red_smem, T& result) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = om_warp_reduce<OP>(v);
+  if (lane == 0) red_smem[wid] = v;
+  __syncthreads();
+  const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  __shared__ bool is_last;
+  if (wid == 0) {
+    T w = (lane < NT / 32) ? red_smem[lane] : identity;
+    w = om_warp_reduce<OP>(w);
+    if (lane == 0) {
+      partials[bid] = w;
+      __threadfence();
+      unsigned prev = atomicAdd(counter, 1u);
+      is_last = (prev == nblk - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  // the last CTA folds all partials in a fixed order (deterministic for a given grid)
+  T acc = identity;
+  for (unsigned i = threadIdx.x; i < nblk; i += NT) acc = OP::op(acc, ((volatile T*)partials)[i]);
+  acc = om_warp_reduce<OP>(acc);
+  __syncthreads();
+  if (lane == 0) red_smem[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    T w = (lane < NT / 32) ? red_smem[lane] : identity;
+    w = om_warp_reduce<OP>(w);
+    if (lane == 0) {
+      result = w;
+      return true;
+    }
+  }
+  return false;
+}
+
+// ---- fast-math build only (Setup.fast_math): division / square root without the IEEE slow path ------------
+// MUFU-seeded Newton iterations, then one residual correction: results are within 1 ulp of the correctly
+// rounded value for normal operands (no denormal / inf / NaN handling).  The default build does not use these:
+// it keeps IEEE division and square root so that results are bit-identical to the reference's C++.
+#ifndef OM_EMULATED_INTRINSICS
+__device__ __forceinline__ double om_frcp(double b) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));     // ~20 correct bits (MUFU.RCP64H)
+  const double e = fma(-b, y, 1.0);                          // |e| <= 2^-20
+  return fma(y, fma(e, e, e), y);                            // y (1 + e + e^2): cubic step, relative error e^3 + rounding
+}
+__device__ __forceinline__ double om_rsqrt_seed(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // ~20 correct bits (MUFU.RSQ64H)
+  return y;
+}
+// std::max / std::min as a compare + select that the compiler cannot canonicalise into max.f64 / min.f64:
+// sm_100a has no DMNMX and lowers those to 7 instructions (DSETP.MAX, 3 moves, FSEL, SEL, LOP3 NaN fix-up).
+__device__ __forceinline__ double om_fmax_std(double a, double b) {            // (a < b) ? b : a
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+__device__ __forceinline__ double om_fmin_std(double a, double b) {            // (b < a) ? b : a
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+#else
+static inline double om_frcp(double b) { return 1.0 / b; }
+static inline double om_fmax_std(double a, double b) { return (a < b) ? b : a; }
+static inline double om_fmin_std(double a, double b) { return (b < a) ? b : a; }
+static inline double om_rsqrt_seed(double x) { return 1.0 / sqrt(x); }
+#endif
+__device__ __forceinline__ double om_fdiv_r(double a, double b, double rb) {   // a / b given rb = 1/b (<= 1 ulp): <= 1.5 ulp
+  (void)b;
+  return a * rb;
+}
+__device__ __forceinline__ double om_fsqrt(double x) {
+  // Coupled (Goldschmidt) iteration g -> sqrt(x), h -> 1/(2 sqrt(x)) from the 20-bit seed, then one residual correction:
+  // 7 FP64 instructions + MUFU, <= 1 ulp.  The clamp only feeds the seed, so x == 0 -> g = 0 * seed = 0 exactly.
+  const double y = om_rsqrt_seed(om_fmax_std(1e-300, x));
+  double g = x * y, h = 0.5 * y;
+  const double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);                            // ~40 bits
+  h = fma(h, r, h);
+  return fma(fma(-g, g, x), h, g);
+}
+__device__ __forceinline__ float om_frcp(float b) { return 1.0f / b; }
+__device__ __forceinline__ float om_fdiv_r(float a, float b, float rb) { (void)rb; return a / b; }
+__device__ __forceinline__ float om_fsqrt(float x) { return sqrtf(x); }
+
+// wrap an index into [0, n) assuming it is at most one period out of range
+__device__ __forceinline__ int om_wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+#define OM_CUDA_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)

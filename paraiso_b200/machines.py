@@ -34,6 +34,19 @@ def build_hydro_exampled(verbose: bool = False):
     return build_machine(hydro_setup(), hydro_om("exampled"), tag="HydroExampled_OO_Float", verbose=verbose)
 
 
+def build_helloworld(verbose: bool = False):
+    """examples/HelloWorld/Generator.hs (and examples/HelloGPU, the same program with language = CUDA): class TableMaker."""
+    from .examples.helloworld import helloworld_om, helloworld_setup
+    return build_machine(helloworld_setup(), helloworld_om(), tag="TableMaker_Hello", verbose=verbose)
+
+
+def build_shiftexample(cyclic: bool, verbose: bool = False):
+    """examples/ShiftExample/Generator.hs (rank 1; dist-open / dist-cyclic): class TableMaker."""
+    from .examples.shiftexample import shiftexample_om, shiftexample_setup
+    return build_machine(shiftexample_setup(cyclic), shiftexample_om(), tag="TableMaker_Shift" + ("C" if cyclic else "O"),
+                         verbose=verbose)
+
+
 def life_machine(size, device="cuda", **kw) -> Machine:
     desc, so = build_life()
     return Machine(desc, so, size=size, device=device, **kw)

@@ -1,0 +1,33 @@
+"""Regenerate tests/golden/driver_*.txt: stdout of the reference's own example drivers (examples/HelloWorld/main.cpp,
+examples/ShiftExample/main.cpp for dist-open and dist-cyclic, examples/Life/main.cpp's first frames) compiled unchanged
+against the oracle's reference-style C++ class (oracle/plantrans.py) and run on the CPU.
+
+    python tests/golden/make_driver_goldens.py        (needs /root/reference; run in the build container)
+
+examples/HelloGPU/main.cu is the HelloWorld driver again (same program, language = CUDA): it shares driver_helloworld.txt.
+"""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests import refdrivers  # noqa: E402
+
+
+def main():
+    with tempfile.TemporaryDirectory() as tmp:
+        for key in refdrivers.KEYS:
+            exe = refdrivers.link_oracle(key, tmp)
+            text = refdrivers.run(key, exe)
+            path = refdrivers.golden_path(key)
+            if key == "hellogpu":
+                assert text == open(path).read(), "HelloGPU driver output differs from HelloWorld's"
+                continue
+            with open(path, "w") as f:
+                f.write(text)
+            print(path, len(text), "bytes")
+
+
+if __name__ == "__main__":
+    main()
