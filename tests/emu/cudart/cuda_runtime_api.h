@@ -1,8 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — a host-memory stand-in for the handful of CUDA runtime calls the GENERATED HOST CLASS
 // (<Name>.cpp) makes, so that the class (lazy mirrors, dirty tracking, pitched <-> reference layout copies, stage
 // geometry) can be exercised together with the emulated kernels (tests/emu/cuda_emu.h) on a machine without a GPU.
-// "Device" memory is malloc'ed host memory, streams and events are no-ops (every call completes immediately), one
-// device is visible.  Nothing in paraiso_b200/ includes this file: the product links the real libcudart.
+// "Device" memory is malloc'ed host memory, streams and events are no-ops (every call completes immediately).  Nothing in paraiso_b200/ includes this file: the product links the real libcudart.
 #pragma once
 #include <cstdlib>
 #include <cstring>
@@ -16,8 +15,10 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime error"; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+// OM_EMU_DEVICES=N in the environment: N "devices" (all of them host memory; tests/emu/cudart/nccl.h moves data between them)
+static inline int om_emu_device_count() { const char* e = std::getenv("OM_EMU_DEVICES"); const int n = e ? std::atoi(e) : 1; return n > 0 ? n : 1; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = om_emu_device_count(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < om_emu_device_count() ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }   // four "SMs"
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
