@@ -108,6 +108,21 @@ def test_cpp_classes_on_several_gpus_equal_one_gpu(gpus):
     assert _run(hydro_fast, 6, gpus) == _run(hydro_fast, 6, 1)
 
 
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_rank3_cpp_class_on_several_gpus_equals_one_gpu(gpus):
+    """Rank-3 machines are cut along axis 2 (whole ghost planes by ncclSend/ncclRecv); same printed numbers as one GPU."""
+    import torch
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.rank3 import life3d_om
+    from paraiso_b200.generator.native import Setup
+    setup = Setup(local_size=(48, 20, 12), boundary=("Cyclic", "Cyclic", "Cyclic"))
+    build_machine(setup, life3d_om(), tag="Life3_host")
+    exe = build_driver("Life3", "Life3_host", "life3_driver.cpp")
+    assert _run(exe, 6, gpus) == _run(exe, 6, 1)
+
+
 def test_cpp_class_rejects_more_gpus_than_visible():
     from paraiso_b200.machines import build_life
     build_life()
