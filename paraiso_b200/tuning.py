@@ -57,8 +57,14 @@ def measure(m: Machine, kernel: str, steps: int = 30, warmup: int = 5, stage: in
 
 
 def grid_search(make_setup: Callable[[], Setup], make_om: Callable, cands: List[Tuning], size, kernel: str = "proceed",
-                stage: int = None, prepare: Callable[[Machine], None] = None, fmad: bool = False, steps: int = 30) -> List[dict]:
-    """Generate + nvcc + time every candidate; returns [{tuning, ms, cells_per_s, occupancy, smem}] best first."""
+                stage: int = None, prepare: Callable[[Machine], None] = None, fmad: bool = False, steps: int = 30,
+                prune_to: int = 0) -> List[dict]:
+    """Generate + nvcc + time every candidate; returns [{tuning, ms, cells_per_s, occupancy, smem}] best first.
+    `prune_to` > 0: only the candidates the static cost model (costmodel.py: SASS instruction mix, registers, shared
+    memory -> predicted cycles per cell; no GPU time) ranks among its best `prune_to` are timed."""
+    if prune_to and len(cands) > prune_to:
+        from .costmodel import prune
+        cands = prune(make_setup, make_om, cands, size, keep=prune_to, kernel=kernel, stage=-1 if stage is None else stage, fmad=fmad)
     results = []
     for t in cands:
         setup = make_setup()
