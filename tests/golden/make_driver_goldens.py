@@ -4,6 +4,8 @@ against the oracle's reference-style C++ class (oracle/plantrans.py) and run on 
 
     python tests/golden/make_driver_goldens.py        (needs /root/reference; run in the build container)
 
+examples/Hydro/main-kh.cpp (1024^2 double, runs to t = 1) is stopped after its first snapshot: driver_hydro.json holds the
+printed times and a numeric digest of the snapshot.
 examples/HelloGPU/main.cu is the HelloWorld driver again (same program, language = CUDA): it shares driver_helloworld.txt.
 """
 import os
@@ -27,6 +29,12 @@ def main():
             with open(path, "w") as f:
                 f.write(text)
             print(path, len(text), "bytes")
+        import json
+        got = refdrivers.run_hydro(refdrivers.link_oracle_hydro(tmp))
+        with open(os.path.join(refdrivers.GOLDEN, "driver_hydro.json"), "w") as f:
+            json.dump(dict(_comment="examples/Hydro/main-kh.cpp, unchanged, on the oracle's reference-style class (1024^2 double): "
+                                    "first printed times, column sums and diagonal cells of output1/snapshot0000.txt", **got), f, indent=1)
+        print(got)
 
 
 if __name__ == "__main__":

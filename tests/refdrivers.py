@@ -159,5 +159,77 @@ def run(key: str, exe: str, seconds: float = 120.0) -> str:
             return life_frames(f.read())
 
 
+# ---- examples/Hydro/main-kh.cpp: integrates 1024^2 to t = 1 and writes 101 snapshots; the first one is compared --------------
+HYDRO_TIMES = 4        # lines of the driver's stderr (sim.time() before each proceed()) that are compared
+
+
+def _hydro_setup_om():
+    from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+    return hydro_setup(), hydro_om("master")
+
+
+def link_b200_hydro() -> str:
+    from paraiso_b200.machines import build_hydro
+    _desc, so = build_hydro()
+    d = os.path.dirname(so)
+    os.makedirs(OUT, exist_ok=True)
+    exe = exe_path("hydro")
+    cmd = [_cxx(), "-std=c++17", "-O1", "-w", f"-I{d}", f"-I{CUDA}/include", os.path.join(REF, "examples/Hydro/main-kh.cpp"),
+           os.path.join(d, "Hydro.cpp"), f"-L{d}", "-lom_Hydro", f"-L{CUDA}/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{d}", "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def link_oracle_hydro(outdir: str) -> str:
+    from oracle import plantrans
+    from paraiso_b200.generator.plan import translate
+    setup, om = _hydro_setup_om()
+    hdr = os.path.join(outdir, "hdr_hydro")
+    os.makedirs(hdr, exist_ok=True)
+    with open(os.path.join(hdr, "Hydro.hpp"), "w") as f:
+        f.write(plantrans.emit(translate(setup, om)))
+    exe = os.path.join(outdir, "oracle_hydro")
+    subprocess.run([_cxx(), "-std=c++17", "-O2", "-fopenmp", "-w", "-ffp-contract=off", f"-I{hdr}",
+                    os.path.join(REF, "examples/Hydro/main-kh.cpp"), "-o", exe], check=True)
+    return exe
+
+
+def run_hydro(exe: str, seconds: float = 600.0) -> dict:
+    """Run main-kh.cpp until it has printed HYDRO_TIMES + 1 times (the first snapshot, written after the second proceed(),
+    is complete by then), stop it, return the printed times and a digest of output1/snapshot0000.txt (1024^2 lines
+    `x y density velocity0 velocity1 pressure`, six significant digits): column sums and the cells (64 k, 64 k)."""
+    import time
+    with tempfile.TemporaryDirectory() as cwd:
+        err_path = os.path.join(cwd, "stderr.txt")
+        with open(err_path, "w") as err:
+            p = subprocess.Popen([exe], cwd=cwd, stdout=subprocess.DEVNULL, stderr=err)
+            t0 = time.time()
+            try:
+                while time.time() - t0 < seconds:
+                    if p.poll() is not None:
+                        raise RuntimeError(f"Hydro driver exited by itself ({p.returncode}): {open(err_path).read()[-2000:]}")
+                    with open(err_path) as f:
+                        if f.read().count("\n") >= HYDRO_TIMES + 1:
+                            break
+                    time.sleep(0.05)
+                else:
+                    raise RuntimeError("Hydro driver too slow")
+            finally:
+                if p.poll() is None:
+                    p.kill()
+                    p.wait()
+        with open(err_path) as f:
+            times = f.read().split("\n")[:HYDRO_TIMES]
+        import numpy as np
+        with open(os.path.join(cwd, "output1", "snapshot0000.txt")) as f:
+            a = np.fromstring(f.read(), sep=" ").reshape(-1, 6)      # x y density velocity0 velocity1 pressure
+        n = int(round(len(a) ** 0.5))
+        # (no hash of the text: the driver's init() evaluates sin on the device, <= 2 ulp from libm's, and the near-zero
+        #  velocities are printed with six digits — the comparison is numeric, see tests/test_gpu_reference_drivers.py)
+        return dict(times=times, cells=len(a), column_sums=[float(v) for v in a.sum(axis=0)],
+                    abs_sums=[float(v) for v in np.abs(a).sum(axis=0)],
+                    diagonal=[[float(v) for v in a[i * n + i]] for i in range(0, n, 64)])
+
+
 def golden_path(key: str) -> str:
     return os.path.join(GOLDEN, f"driver_{'helloworld' if key == 'hellogpu' else key}.txt")

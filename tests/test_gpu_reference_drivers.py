@@ -21,3 +21,27 @@ def test_reference_driver_prints_the_reference_output(key):
         want = f.read()
     got = refdrivers.run(key, exe)
     assert got == want
+
+
+def test_hydro_reference_driver_first_snapshot():
+    """examples/Hydro/main-kh.cpp, unchanged, on the B200 class (bit-exact build): the times it prints and its first
+    snapshot file against the same driver on the reference-style class.  The driver's own init() evaluates sin on the
+    device (<= 2 ulp from libm's, DESIGN §5 deviation 5) and the snapshot holds six significant digits, so the
+    comparison is numeric: printed times identical, column sums within 2e-6 of the absolute sums, sampled cells within
+    1e-4 relative."""
+    import json
+    exe = refdrivers.exe_path("hydro")
+    if not os.path.exists(exe):
+        if not os.path.isdir(refdrivers.REF):
+            pytest.skip("driver not prebuilt and /root/reference not mounted")
+        exe = refdrivers.link_b200_hydro()
+    with open(os.path.join(refdrivers.GOLDEN, "driver_hydro.json")) as f:
+        want = json.load(f)
+    got = refdrivers.run_hydro(exe)
+    assert got["times"] == want["times"]
+    assert got["cells"] == want["cells"] == 1024 * 1024
+    for g, w, a in zip(got["column_sums"], want["column_sums"], want["abs_sums"]):
+        assert abs(g - w) <= 2e-6 * a + 1e-12
+    for grow, wrow in zip(got["diagonal"], want["diagonal"]):
+        for g, w in zip(grow, wrow):
+            assert abs(g - w) <= 1e-4 * abs(w) + 1e-13

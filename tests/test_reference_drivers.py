@@ -90,3 +90,15 @@ def test_life_golden_matches_an_independent_life():
         n = sum(np.roll(np.roll(c, dy, 0), dx, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0))
         c = (((c == 0) & (n == 3)) | ((c == 1) & (n >= 2) & (n <= 3))).astype(np.int64)
         pop = int(c.sum())
+
+
+@needs_reference
+def test_hydro_golden_is_what_the_oracle_class_prints(tmp_path):
+    """examples/Hydro/main-kh.cpp on the reference-style class: dt of the first steps (7.3982e-05: the value the reference's
+    own float sample reaches, tests/golden/hydro_exampled.json: time 0.00073982 after ten steps) and the snapshot digest."""
+    import json
+    with open(os.path.join(refdrivers.GOLDEN, "driver_hydro.json")) as f:
+        want = json.load(f)
+    assert want["times"][:2] == ["0", "7.3982e-05"]
+    got = refdrivers.run_hydro(refdrivers.link_oracle_hydro(str(tmp_path)))
+    assert got["times"] == want["times"] and got["column_sums"] == want["column_sums"] and got["diagonal"] == want["diagonal"]
