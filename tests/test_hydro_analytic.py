@@ -72,6 +72,45 @@ def test_entropy_wave_converges_and_matches_oracle():
     assert errs[64] < 2e-3, errs
 
 
+# ---- sound wave (attic/GA.reproduce/massive-test.cu:67-83): linear acoustic wave, gamma = 5/3, c = 1, amplitude 1e-5 -----------
+def sound_wave(n, t_end, machine_cls, ny=8):
+    """rho = g + g v, p = 1 + g v, v = a sin 2 pi (x - t) with g = 5/3 (so c = sqrt(g p / rho) = 1): a right-going simple wave,
+    exact to first order in the amplitude a = 1e-5 (the neglected steepening is O(a^2 t) = 1e-10 relative to a)."""
+    size = (n, ny)
+    setup = hydro_setup(size, periodic=True)
+    m = machine_cls(setup)
+    g, a = 5.0 / 3.0, 1e-5
+    xs = (np.arange(n) + 0.5) / n
+    X = np.tile(xs, (ny, 1))
+    vx = lambda x, t: a * np.sin(2 * np.pi * (x - t))
+    m.setp(dict(time=0.0, cfl=0.4, extent0=1.0, extent1=ny / n, dR0=1.0 / n, dR1=1.0 / n))
+    m.seta("density", g + g * vx(X, 0.0)); m.seta("velocity0", vx(X, 0.0)); m.seta("velocity1", np.zeros((ny, n)))
+    m.seta("pressure", 1.0 + g * vx(X, 0.0))
+    steps = 0
+    while m.time() < t_end and steps < 10000:
+        m.step()
+        steps += 1
+    t = m.time()
+    err = np.mean(np.abs(m.geta("velocity0") - vx(X, t))) / a
+    return m, err, steps
+
+
+def test_sound_wave_propagates_at_the_sound_speed_and_converges():
+    t_end = 0.25
+    errs = {}
+    for n in (32, 64, 128):
+        m, errs[n], steps = sound_wave(n, t_end, Emu)
+        if n == 64:
+            o, err_o, steps_o = sound_wave(n, t_end, Orc)
+            assert steps == steps_o and m.time() == o.time()
+            for name in ("density", "velocity0", "velocity1", "pressure"):
+                assert np.array_equal(m.geta(name).view(np.uint64), o.geta(name).view(np.uint64)), name
+        assert np.max(np.abs(m.geta("velocity1"))) < 1e-12          # stays one-dimensional
+    # relative L1 error of the velocity perturbation: better than second order between refinements, 1 % at 128 cells
+    assert errs[64] < errs[32] / 2.4 and errs[128] < errs[64] / 2.4, errs
+    assert errs[128] < 1e-2, errs
+
+
 # ---- Sod shock tube (the reference's second exam, attic/GA.reproduce/massive-test.cu:120-174 with riemann-solver.h) -----------
 def riemann_exact(rl, ul, pl, rr, ur, pr, g, xi):
     """Exact solution of the Riemann problem for the ideal-gas Euler equations sampled at xi = x / t
