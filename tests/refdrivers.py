@@ -50,8 +50,13 @@ def _incdir(header_dir: str, prefix: str) -> str:
     """A directory from which `#include "<prefix>/<Name>.hpp"` resolves to header_dir/<Name>.hpp."""
     if not prefix:
         return header_dir
-    t = tempfile.mkdtemp(prefix="om_inc_")
-    os.symlink(header_dir, os.path.join(t, prefix))
+    t = os.path.join(OUT, "inc_" + os.path.basename(header_dir.rstrip("/")))
+    os.makedirs(t, exist_ok=True)
+    link = os.path.join(t, prefix)
+    if os.path.islink(link) and os.readlink(link) != header_dir:
+        os.unlink(link)
+    if not os.path.islink(link):
+        os.symlink(header_dir, link)
     return t
 
 
