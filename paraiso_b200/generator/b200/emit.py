@@ -98,7 +98,7 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
     slot = nstat
     for k in om.kernels:
         ks = schedule_kernel(om, k, slot, setup.tuning.mat_threshold, setup.tuning.mat_flip, setup.tuning.carry_reduces, setup.tuning.planes_per_cta,
-                             setup.tuning.sink_selects, bool(setup.fast_math) and setup.tuning.fast_algebra)
+                             setup.tuning.sink_selects, bool(setup.fast_math) and setup.tuning.fast_algebra, setup.tuning.pull_shifts)
         slot += len(ks.reduce_slots) + ks.extra_slots
         schedules.append(ks)
     cu: List[str] = [

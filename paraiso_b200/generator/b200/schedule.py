@@ -540,10 +540,10 @@ def find_carry(ops: Dict[int, Op], rl: Dict[int, int], reduce_slots: Dict[int, i
 
 def schedule_kernel(om: OM, kernel: Kernel, slot_base: int, mat_threshold: int = MAT_THRESHOLD, mat_flip=(),
                     carry_reduces: bool = True, zplanes: int = 1, sink_selects: bool = True,
-                    fast_algebra: bool = False) -> KernelSchedule:
+                    fast_algebra: bool = False, pull_shifts: bool = False) -> KernelSchedule:
     g = kernel.dataflow
     dim = om.dim
-    ops, stores = fold_ops(g, dim)
+    ops, stores = fold_ops(g, dim, pull_shifts=pull_shifts)
     sink_stats = None
     if fast_algebra:
         from .selectsink import simplify_fast
