@@ -263,7 +263,9 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": kinfo["stages"][dom]["symbol"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_cell": alg_bytes, "kernel_ms": kms},
-                "e2e": {"value": e2e_value, "unit": "Gcell/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+                # (h2d_gbs: the state upload alone bounds the end-to-end step — PCIe, not the kernel)
+                "e2e": {"value": e2e_value, "unit": "Gcell/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                        "ms_per_step": ems / esteps, "h2d_gbs": h2d / (ems / esteps * 1e-3) / 1e9},
                 "gpu_launches": launches, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:   # the CPU leg runs at N = 1 only (ranks of a multi-GPU job do not wait for it)
             sample = (4096, 4096) if args.workload == "life" else (1024, 1024)
