@@ -115,6 +115,30 @@ def time_cpu(workload: str, size, steps: int, warmup: int):
     return size[0] * size[1] * steps / dt / 1e9, dt / steps * 1e3
 
 
+def fp64_roofline(m, stage: int, kernel_ms: float, clocks):
+    """{"achieved", "peak", "unit", "frac", ...} of the FP64 pipe for one launch of proceed's stage `stage`, or None when
+    cuobjdump is not available.  Static instruction counts come from paraiso_b200.costmodel (the SASS of the loaded library)."""
+    try:
+        from paraiso_b200 import costmodel
+        e = costmodel.estimate_stage(m.desc, m.lib._name, kernel="proceed", stage=stage, size=(m.nx, m.nyl))
+        sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        sms = 148
+        try:
+            import torch
+            sms = torch.cuda.get_device_properties(m.device).multi_processor_count
+        except Exception:
+            pass
+        warp_rows = m.nx * m.nyl / 32.0 * e.overhead
+        achieved = warp_rows * e.fp64 / (kernel_ms * 1e-3) / 1e9          # G warp-instructions / s
+        peak = sms * 4 * 0.5 * sm_hz / 1e9
+        return {"bound": "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s", "frac": achieved / peak,
+                "fp64_instr_per_warp_row": e.fp64, "instr_per_warp_row": e.instructions, "overhead": e.overhead,
+                "registers": e.registers, "ctas_per_sm": e.ctas_per_sm,
+                "source": "static SASS count of the row loop (cuobjdump) x measured kernel time; ncu: profiles/r1i_hydro_fast_ncu.txt"}
+    except Exception as ex:     # measurement garnish only: never lose the bench line over it
+        return {"bound": "fp64_pipe", "unavailable": repr(ex)[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -236,6 +260,11 @@ def main():
         with open(tpath) as f:
             traffic = json.load(f).get(kinfo["stages"][dom]["symbol"] + ("_fast" if args.fast else ""), {}).get("dram_bytes_per_launch")
 
+    # Hydro's flux kernel is bound by the FP64 pipe, not by HBM — report that roof next to the HBM fraction.
+    # FP64 warp instructions per launch = static count in the row loop (cuobjdump) x warp-rows x halo / warm-up overhead;
+    # the pipe takes one warp instruction every two cycles per scheduler (64 FP64 lanes per SM).
+    fp64_pipe = fp64_roofline(m, dom, kms, clocks) if args.workload.startswith("hydro") else None
+
     # end to end through the public host API: pinned host state -> device, proceed(), result scalar -> host
     pinned = {n: torch.from_numpy(np.ascontiguousarray(m.get(n))).pin_memory() for n in state}
     h2d = sum(t.numel() * t.element_size() for t in pinned.values())
@@ -262,7 +291,7 @@ def main():
                                      "fmad=true" if args.fmad else "fmad=false (bit-exact vs reference C++)")},
                 "roofline": {"bound": "hbm", "kernel": kinfo["stages"][dom]["symbol"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_cell": alg_bytes, "kernel_ms": kms},
+                             "algorithmic_bytes_per_cell": alg_bytes, "kernel_ms": kms, "fp64_pipe": fp64_pipe},
                 # (h2d_gbs: the state upload alone bounds the end-to-end step — PCIe, not the kernel)
                 "e2e": {"value": e2e_value, "unit": "Gcell/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                         "ms_per_step": ems / esteps, "h2d_gbs": h2d / (ems / esteps * 1e-3) / 1e9},
