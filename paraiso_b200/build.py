@@ -63,15 +63,22 @@ def compile_kernels(d: str, name: str, fmad: bool = False, verbose: bool = False
         h = hashlib.sha1(f.read() + r.read() + " ".join(flags).encode()).hexdigest()
     if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == h:
         return so
-    cmd = [nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + [cu, "-o", so]
+    # several ranks of one job may get here at once (torchrun on a tree that was not prebuilt): build into a private file
+    # and rename, so that nobody ever dlopens a half-written library
+    tmp = f"{so}.tmp{os.getpid()}"
+    cmd = [nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + [cu, "-o", tmp]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, so)
     if verbose:
         with open(os.path.join(d, f"ptxas_{name}{'_fma' if fmad else ''}.log"), "w") as f:
             f.write(res.stderr)
-    with open(stamp, "w") as f:
+    with open(stamp + f".tmp{os.getpid()}", "w") as f:
         f.write(h)
+    os.replace(stamp + f".tmp{os.getpid()}", stamp)
     return so
 
 
