@@ -35,6 +35,11 @@ def main():
             json.dump(dict(_comment="examples/Hydro/main-kh.cpp, unchanged, on the oracle's reference-style class (1024^2 double): "
                                     "first printed times, column sums and diagonal cells of output1/snapshot0000.txt", **got), f, indent=1)
         print(got)
+        heart = refdrivers.heart_digest(refdrivers.run_heart(refdrivers.link_heart("oracle", tmp)))
+        with open(os.path.join(refdrivers.GOLDEN, "driver_initialcondition.json"), "w") as f:
+            json.dump(dict(_comment="examples/InitialCondition/main.cpp, unchanged, on the oracle's reference-style class: digest of heart.txt "
+                                    "(500 x 500 lines `x y atan(...)`, six significant digits)", **heart), f, indent=1)
+        print({k: v for k, v in heart.items() if k != "samples"})
 
 
 if __name__ == "__main__":

@@ -236,5 +236,59 @@ def run_hydro(exe: str, seconds: float = 600.0) -> dict:
                     diagonal=[[float(v) for v in a[i * n + i]] for i in range(0, n, 64)])
 
 
+# ---- examples/InitialCondition/main.cpp: writes heart.txt (`x y table(x,y)` for 500 x 500 cells) -------------------------------
+def _heart():
+    from paraiso_b200.examples.initialcondition import initialcondition_om, initialcondition_setup
+    return "TableMaker", "examples/InitialCondition/main.cpp", "dist", initialcondition_setup, initialcondition_om
+
+
+def link_heart(kind: str, outdir: str = None) -> str:
+    """kind = "b200" (real class + libom), "oracle" (reference-style class) or "emulated" (generated class, emulated kernels)."""
+    name, driver, prefix, mk_setup, mk_om = _heart()
+    if kind == "b200":
+        from paraiso_b200.build import build_machine
+        _desc, so = build_machine(mk_setup(), mk_om(), tag="Heart_OO")
+        d = os.path.dirname(so)
+        os.makedirs(OUT, exist_ok=True)
+        exe = exe_path("initialcondition")
+        cmd = [_cxx(), "-std=c++17", "-O1", "-w", f"-I{_incdir(d, prefix)}", f"-I{d}", f"-I{CUDA}/include", os.path.join(REF, driver),
+               os.path.join(d, f"{name}.cpp"), f"-L{d}", f"-lom_{name}", f"-L{CUDA}/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{d}", "-o", exe]
+    elif kind == "oracle":
+        from oracle import plantrans
+        from paraiso_b200.generator.plan import translate
+        hdr = os.path.join(outdir, "hdr_heart")
+        os.makedirs(os.path.join(hdr, prefix), exist_ok=True)
+        with open(os.path.join(hdr, prefix, f"{name}.hpp"), "w") as f:
+            f.write(plantrans.emit(translate(mk_setup(), mk_om())))
+        exe = os.path.join(outdir, "oracle_heart")
+        cmd = [_cxx(), "-std=c++17", "-O1", "-w", "-ffp-contract=off", f"-I{hdr}", os.path.join(REF, driver), "-o", exe]
+    else:
+        from tests.emu.build_emu import build_emulated
+        _desc, so = build_emulated(mk_setup(), mk_om(), tag="Heart_ref")
+        d = os.path.dirname(so)
+        exe = os.path.join(outdir, "emu_heart")
+        cmd = [_cxx(), "-std=c++20", "-O1", "-w", "-DOM_B200_NO_NCCL", f"-I{os.path.join(ROOT, 'tests', 'emu', 'cudart')}",
+               f"-I{_incdir(d, prefix)}", f"-I{d}", "-x", "c++", os.path.join(REF, driver), os.path.join(d, f"{name}.cpp"), "-x", "none",
+               so, f"-Wl,-rpath,{d}", "-pthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-3000:])
+    return exe
+
+
+def run_heart(exe: str) -> str:
+    with tempfile.TemporaryDirectory() as cwd:
+        subprocess.run([exe], cwd=cwd, check=True, timeout=300)
+        with open(os.path.join(cwd, "heart.txt")) as f:
+            return f.read()
+
+
+def heart_digest(text: str) -> dict:
+    import numpy as np
+    a = np.fromstring(text, sep=" ").reshape(-1, 3)
+    return dict(cells=len(a), column_sums=[float(v) for v in a.sum(axis=0)], abs_sum=float(np.abs(a[:, 2]).sum()),
+                samples=[[float(v) for v in a[i]] for i in range(0, len(a), 5003)])
+
+
 def golden_path(key: str) -> str:
     return os.path.join(GOLDEN, f"driver_{'helloworld' if key == 'hellogpu' else key}.txt")

@@ -45,3 +45,22 @@ def test_hydro_reference_driver_first_snapshot():
     for grow, wrow in zip(got["diagonal"], want["diagonal"]):
         for g, w in zip(grow, wrow):
             assert abs(g - w) <= 1e-4 * abs(w) + 1e-13
+
+
+def test_initialcondition_reference_driver():
+    """examples/InitialCondition/main.cpp on the B200 class: heart.txt against the reference-style class's digest.  atan, exp
+    and log are CUDA's (<= 2 ulp from libm's) and the file holds six digits: numeric comparison."""
+    import json
+    exe = refdrivers.exe_path("initialcondition")
+    if not os.path.exists(exe):
+        if not os.path.isdir(refdrivers.REF):
+            pytest.skip("driver not prebuilt and /root/reference not mounted")
+        exe = refdrivers.link_heart("b200")
+    with open(os.path.join(refdrivers.GOLDEN, "driver_initialcondition.json")) as f:
+        want = json.load(f)
+    got = refdrivers.heart_digest(refdrivers.run_heart(exe))
+    assert got["cells"] == want["cells"]
+    for g, w in zip(got["column_sums"], want["column_sums"]):
+        assert abs(g - w) <= 2e-6 * want["abs_sum"] + 1e-9 * abs(w)
+    for grow, wrow in zip(got["samples"], want["samples"]):
+        assert grow[:2] == wrow[:2] and abs(grow[2] - wrow[2]) <= 1e-5 * abs(wrow[2]) + 1e-9

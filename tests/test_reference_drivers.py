@@ -102,3 +102,18 @@ def test_hydro_golden_is_what_the_oracle_class_prints(tmp_path):
     assert want["times"][:2] == ["0", "7.3982e-05"]
     got = refdrivers.run_hydro(refdrivers.link_oracle_hydro(str(tmp_path)))
     assert got["times"] == want["times"] and got["column_sums"] == want["column_sums"] and got["diagonal"] == want["diagonal"]
+
+
+@needs_reference
+def test_initialcondition_driver_compiles_and_prints_the_oracle_output(tmp_path):
+    """examples/InitialCondition/main.cpp (cast, ^, **, atan on a 500 x 500 grid, written to heart.txt): compiles unchanged
+    against the generated class; with emulated kernels the file is byte-identical to the reference-style class's (both
+    sides use the host's libm), whose digest is the committed golden."""
+    import json
+    assert os.access(refdrivers.link_heart("b200"), os.X_OK)
+    want_text = refdrivers.run_heart(refdrivers.link_heart("oracle", str(tmp_path)))
+    with open(os.path.join(refdrivers.GOLDEN, "driver_initialcondition.json")) as f:
+        want = json.load(f)
+    got = refdrivers.heart_digest(want_text)
+    assert got["cells"] == want["cells"] == 250000 and got["column_sums"] == want["column_sums"] and got["samples"] == want["samples"]
+    assert refdrivers.run_heart(refdrivers.link_heart("emulated", str(tmp_path))) == want_text
