@@ -263,7 +263,7 @@ def main():
     # Hydro's flux kernel is bound by the FP64 pipe, not by HBM — report that roof next to the HBM fraction.
     # FP64 warp instructions per launch = static count in the row loop (cuobjdump) x warp-rows x halo / warm-up overhead;
     # the pipe takes one warp instruction every two cycles per scheduler (64 FP64 lanes per SM).
-    fp64_pipe = fp64_roofline(m, dom, kms, clocks) if args.workload.startswith("hydro") else None
+    fp64_pipe = fp64_roofline(m, dom, kms, clocks) if (rank == 0 and args.workload.startswith("hydro")) else None
 
     # end to end through the public host API: pinned host state -> device, proceed(), result scalar -> host
     pinned = {n: torch.from_numpy(np.ascontiguousarray(m.get(n))).pin_memory() for n in state}
