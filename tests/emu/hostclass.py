@@ -25,3 +25,47 @@ def link_emulated(setup, om, tag: str, driver: str, exe: str, include_dirs=()):
 def run(exe: str, args=(), devices: int = 1, timeout: float = 600.0) -> str:
     env = dict(os.environ, OM_EMU_DEVICES=str(devices), OM_B200_GPUS=str(devices))
     return subprocess.run([exe, *map(str, args)], check=True, capture_output=True, text=True, env=env, timeout=timeout).stdout
+
+
+def link_tsan(setup, om, tag: str, driver: str, exe: str, drop_barrier: int = None, kernel_marker: str = None):
+    """The same link with ThreadSanitizer over the emulated kernels (CUDA threads are host threads, __syncthreads is a
+    std::barrier): a missing barrier between a shared-memory ring's writers and readers is a reported data race.
+    `drop_barrier` = n removes the n-th `__syncthreads();` after `kernel_marker` in the generated kernel source — the
+    negative control that shows the detector sees the rings.  Returns None when the toolchain has no TSan runtime."""
+    desc, so = build_emulated(setup, om, tag=tag)
+    d = os.path.dirname(so)
+    name = desc["name"]
+    cu = os.path.join(d, f"{name}_kernels.cu")
+    work = os.path.dirname(exe)
+    if drop_barrier is not None:
+        with open(cu) as f:
+            lines = f.read().split("\n")
+        start = next(i for i, l in enumerate(lines) if kernel_marker in l)
+        sites = [i for i in range(start, len(lines)) if lines[i].strip() == "__syncthreads();"]
+        lines[sites[drop_barrier]] = "    /* barrier removed by the negative control */"
+        cu = os.path.join(work, f"{name}_dropped{drop_barrier}.cu")
+        with open(cu, "w") as f:
+            f.write("\n".join(lines))
+    cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
+    common = [cxx, "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-w", "-pthread"]
+    obj = exe + "_kernels.o"
+    r = subprocess.run(common + ["-c", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", d, "-x", "c++", cu, "-o", obj],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        if "tsan" in r.stderr.lower() or "sanitize" in r.stderr.lower():
+            return None
+        raise RuntimeError(r.stderr[-3000:])
+    r = subprocess.run(common + [f"-I{os.path.join(HERE, 'cudart')}", f"-I{d}", driver, os.path.join(d, f"{name}.cpp"), obj, "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        if "tsan" in r.stderr.lower() or "sanitize" in r.stderr.lower():
+            return None
+        raise RuntimeError(r.stderr[-3000:])
+    return exe
+
+
+def run_tsan(exe: str, args=(), timeout: float = 900.0):
+    """(stdout, number of ThreadSanitizer reports)."""
+    env = dict(os.environ, OM_EMU_DEVICES="1", OM_B200_GPUS="1", TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, env=env, timeout=timeout)
+    return r.stdout, r.stderr.count("WARNING: ThreadSanitizer")
