@@ -58,3 +58,35 @@ def test_rank3_kernels_are_race_free(tmp_path):
                                     str(tmp_path / "diff3_tsan")))
     out, reports = hostclass.run_tsan(exe, [2])
     assert reports == 0 and out.startswith("20 9 8 ")
+
+
+# ---- memory safety: the same executables under AddressSanitizer ("device" arrays are malloc'ed by the runtime stand-in) ----------
+def _asan_cases():
+    from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+    from paraiso_b200.examples.life import life_om, life_setup
+    from paraiso_b200.examples.rank3 import diffusion3d_om
+    from paraiso_b200.generator.native import Setup
+    return {"life": (life_setup("master"), life_om("master"), "Life_hostclass", "life_driver.cpp", 5),
+            "hydro_fast": (hydro_setup((64, 48), fast=True), hydro_om("master"), "Hydro_hostclass_1", "hydro_driver.cpp", 3),
+            "diff3": (Setup(local_size=(20, 9, 8), boundary=("Open", "Open", "Open")), diffusion3d_om(), "Diff3_hostclass_OOO",
+                      "diff3_driver.cpp", 2)}
+
+
+@pytest.mark.parametrize("case", ["life", "hydro_fast", "diff3"])
+@pytest.mark.parametrize("devices", [1, 3])
+def test_kernels_stay_inside_their_allocations(case, devices, tmp_path):
+    """No access outside an array's allocation: pipeline fill and halo reads stay within the OM_APRON_ROWS slack rows
+    the ABI promises (include/paraiso_b200.h), on one device and on three slabs (thin slabs are the hard case)."""
+    setup, om, tag, driver, steps = _asan_cases()[case]
+    exe = _need(hostclass.link_tsan(setup, om, tag, os.path.join(CPP, driver), str(tmp_path / f"{case}_asan"), sanitizer="address"))
+    out, reports = hostclass.run_tsan(exe, [steps], devices=devices)
+    assert reports == 0 and out.strip()
+
+
+def test_missing_apron_rows_are_reported(tmp_path):
+    """Negative control of the memory check: a host that allocates no slack rows (the ABI asks for OM_APRON_ROWS = 16)
+    makes the Life kernel's pipeline fill read outside the allocation, and AddressSanitizer says so."""
+    setup, om, tag, driver, steps = _asan_cases()["life"]
+    exe = _need(hostclass.link_tsan(setup, om, tag, os.path.join(CPP, driver), str(tmp_path / "life_noapron"), sanitizer="address", apron=0))
+    _out, reports = hostclass.run_tsan(exe, [2])
+    assert reports > 0
