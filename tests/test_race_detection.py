@@ -90,3 +90,31 @@ def test_missing_apron_rows_are_reported(tmp_path):
     exe = _need(hostclass.link_tsan(setup, om, tag, os.path.join(CPP, driver), str(tmp_path / "life_noapron"), sanitizer="address", apron=0))
     _out, reports = hostclass.run_tsan(exe, [2])
     assert reports > 0
+
+
+# ---- synthetic programs (tests/programs.py) through the generated class with a generated driver, under both sanitizers ------------
+@pytest.mark.parametrize("prog", ["multi_reduce", "wide_CO", "wide_OC", "wide_OO", "ring_float", "chain_1d"])
+@pytest.mark.parametrize("sanitizer", ["thread", "address"])
+def test_synthetic_programs_under_sanitizers(prog, sanitizer, tmp_path):
+    """Several reduces per stage and a reduce feeding a later stage, wide asymmetric stencils on mixed boundaries, a float ring
+    read in both axes, a rank-1 chain: no race, no access outside an allocation, and the same printed results as the plain
+    build — on one device and (rank 2) on two slabs."""
+    from tests.emu.build_emu import build_emulated
+    from tests.generic_driver import driver_source
+    from tests.programs import PROGRAMS
+    make_om, setup, kernels = PROGRAMS[prog]
+    tag = f"prog_{prog}"
+    desc, _so = build_emulated(setup, make_om(), tag=tag)
+    drv = str(tmp_path / "driver.cpp")
+    with open(drv, "w") as f:
+        f.write(driver_source(desc, kernels))
+    plain = str(tmp_path / "plain")
+    hostclass.link_emulated(setup, make_om(), tag, drv, plain)
+    want = hostclass.run(plain)
+    assert want.strip()
+    exe = _need(hostclass.link_tsan(setup, make_om(), tag, drv, str(tmp_path / f"san_{sanitizer}"), sanitizer=sanitizer))
+    for devices in ((1, 2) if len(setup.local_size) > 1 else (1,)):
+        out, reports = hostclass.run_tsan(exe, devices=devices)
+        assert reports == 0, (devices, reports)
+        if desc["kernels"][0]["stages"] and prog != "ring_float":        # (a float Sum over two slabs folds in another order)
+            assert out == want, devices
