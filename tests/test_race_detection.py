@@ -73,14 +73,14 @@ def _asan_cases():
 
 
 @pytest.mark.parametrize("case", ["life", "hydro_fast", "diff3"])
-@pytest.mark.parametrize("devices", [1, 3])
-def test_kernels_stay_inside_their_allocations(case, devices, tmp_path):
+def test_kernels_stay_inside_their_allocations(case, tmp_path):
     """No access outside an array's allocation: pipeline fill and halo reads stay within the OM_APRON_ROWS slack rows
     the ABI promises (include/paraiso_b200.h), on one device and on three slabs (thin slabs are the hard case)."""
     setup, om, tag, driver, steps = _asan_cases()[case]
     exe = _need(hostclass.link_tsan(setup, om, tag, os.path.join(CPP, driver), str(tmp_path / f"{case}_asan"), sanitizer="address"))
-    out, reports = hostclass.run_tsan(exe, [steps], devices=devices)
-    assert reports == 0 and out.strip()
+    for devices in (1, 3):
+        out, reports = hostclass.run_tsan(exe, [steps], devices=devices)
+        assert reports == 0 and out.strip(), devices
 
 
 def test_missing_apron_rows_are_reported(tmp_path):
@@ -93,8 +93,9 @@ def test_missing_apron_rows_are_reported(tmp_path):
 
 
 # ---- synthetic programs (tests/programs.py) through the generated class with a generated driver, under both sanitizers ------------
-@pytest.mark.parametrize("prog", ["multi_reduce", "wide_CO", "wide_OC", "wide_OO", "ring_float", "chain_1d"])
-@pytest.mark.parametrize("sanitizer", ["thread", "address"])
+@pytest.mark.parametrize("prog,sanitizer", [("multi_reduce", "thread"), ("wide_CO", "thread"), ("ring_float", "thread"),
+                                            ("wide_OC", "address"), ("wide_OO", "address"), ("ring_float", "address"),
+                                            ("chain_1d", "address")])
 def test_synthetic_programs_under_sanitizers(prog, sanitizer, tmp_path):
     """Several reduces per stage and a reduce feeding a later stage, wide asymmetric stencils on mixed boundaries, a float ring
     read in both axes, a rank-1 chain: no race, no access outside an allocation, and the same printed results as the plain
