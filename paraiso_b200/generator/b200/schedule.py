@@ -136,7 +136,8 @@ def fold_ops(g: Graph, dim: int, normalize: bool = True, pull_shifts: bool = Fal
         payload = inst.arg if inst.op != "Imm" else (repr(inst.arg), inst.imm_type)
         if normalize and inst.op == "Arith" and inst.arg in COMMUTATIVE and len(args) == 2:
             args = sorted(args)
-        key = (inst.op, payload, inst.cast_to, tuple(args), realm, ctype)
+        key = (inst.op, payload, inst.cast_to, tuple(args), realm, ctype,
+               repr(valid) if (inst.op == "Arith" and inst.arg == "Identity") else None)   # an Identity exists to carry its Valid region
         if key in table:
             return table[key]
         table[key] = i
@@ -158,7 +159,13 @@ def fold_ops(g: Graph, dim: int, normalize: bool = True, pull_shifts: bool = Fal
                     vec = tuple(a + b for a, b in zip(vec, ops[src].inst.arg))
                     src = ops[src].args[0]
                 if all(x == 0 for x in vec) or src in indep:
-                    canon[i] = src
+                    if valid is not None and ops[src].valid is not None and valid != ops[src].valid:
+                        # a shifted position-independent value has the same value everywhere but a smaller Valid region
+                        # (BoundaryAnalysis.hs:85-94): where it is stored or reduced, the cells outside that region stay 0
+                        # in the reference.  Keep the region on an Identity node instead of dropping the Shift.
+                        canon[i] = intern(i, Inst("Arith", "Identity"), [src], realm, ctype, valid)
+                    else:
+                        canon[i] = src
                     continue
                 inst = Inst("Shift", vec)
                 args = [src]
