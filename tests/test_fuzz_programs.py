@@ -110,3 +110,72 @@ def test_shifted_immediate_keeps_its_valid_region():
     want = o.array("a")
     assert np.array_equal(m.get("a", with_margin=True).reshape(want.shape), want)
     assert int(m.scalar("s")) == int(o.scalar("s")[0]) == int(want.sum()) != -2 * want.size
+
+
+# ---- the same for Double (bit-exact: the default build has no FMA contraction and IEEE division / sqrt) and for rank 1 / 3 ----------
+def random_float_program(seed: int, dim: int):
+    from paraiso_b200.om.builder import abs_, sqrt
+    rng = random.Random(1000 + seed)
+    a = Named("a", StaticValue(ARRAY, "Double"))
+    b = Named("b", StaticValue(ARRAY, "Double"))
+    s = Named("s", StaticValue(SCALAR, "Double"))
+    use_reduce = rng.random() < 0.6
+    two_stage = use_reduce and rng.random() < 0.5
+    red_op = rng.choice(["Max", "Min"])            # (a floating-point Sum is folded in another order on the device)
+    plan = [rng.random() for _ in range(400)]
+    reach = 3 if dim < 3 else 1
+
+    def kernel():
+        it = iter(plan)
+        nxt = lambda: next(it)
+        leaves = [bind(load(a)), bind(load(b))]
+
+        def expr(depth):
+            r = nxt()
+            if depth == 0 or r < 0.15:
+                c = nxt()
+                if c < 0.75:
+                    return leaves[int(nxt() * 2)]
+                return imm(round(nxt() * 4 - 2, 3), ARRAY, "Double")
+            if r < 0.40:
+                v = tuple(int(nxt() * (2 * reach + 1)) - reach for _ in range(dim))
+                return bind(shift(v, expr(depth - 1)))
+            if r < 0.80:
+                x, y = expr(depth - 1), expr(depth - 1)
+                op = int(nxt() * 7)
+                return bind([x + y, x - y, x * y * 0.25, max_(x, y), min_(x, y), x / (abs_(y) + 1.5), sqrt(abs_(x) + 0.5)][op])
+            x, y, z = expr(depth - 1), expr(depth - 1), expr(depth - 1)
+            return bind(select(lt(x, y), y, z))
+        e1 = bind(expr(3))
+        e2 = bind(expr(3))
+        if use_reduce:
+            r = bind(reduce(red_op, e1))
+            store(s, r)
+            if two_stage:
+                e2 = bind(e2 + broadcast(r) * 0.125)
+        store(a, max_(min_(e2, imm(8.0, ARRAY, "Double")), imm(-8.0, ARRAY, "Double")))
+        store(b, e1 * 0.5)
+    om = lambda: makeOM("FuzzF", [], [a, b, s], [("k", kernel)], dim=dim)
+    sizes = {1: [(257,), (1000,)], 2: [(33, 9), (70, 14), (130, 5)], 3: [(20, 9, 6), (33, 5, 7)]}[dim]
+    return om, Setup(local_size=rng.choice(sizes), boundary=tuple(rng.choice([OPEN, CYCLIC]) for _ in range(dim)))
+
+
+@pytest.mark.parametrize("dim,seed", [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (2, 3), (3, 0), (3, 1), (3, 2)])
+def test_random_float_program_matches_oracle(dim, seed):
+    om, setup = random_float_program(seed, dim)
+    desc, so = build_emulated(setup, om(), tag=f"fuzzf_{dim}_{seed}")
+    m = Machine(desc, so, device="cpu", _emulated=True)
+    o = OracleMachine(setup, om())
+    rng = np.random.default_rng(seed)
+    for name in ("a", "b"):
+        arr = rng.uniform(-2.0, 2.0, o.array(name).shape)
+        o.array(name)[...] = arr
+        m.set(name, arr.reshape(m.get(name, with_margin=True).shape), with_margin=True)
+    for step in range(3):
+        m.call("k"); o.call("k")
+        for st in desc["statics"]:
+            if st["realm"] == "Array":
+                got, want = m.get(st["name"], with_margin=True), o.array(st["name"])
+                assert np.array_equal(got.reshape(want.shape).view(np.uint64), want.view(np.uint64)), (dim, seed, step, st["name"], setup.boundary)
+            else:
+                assert np.float64(m.scalar(st["name"])).view(np.uint64) == o.scalar(st["name"]).view(np.uint64)[0], (dim, seed, step)
