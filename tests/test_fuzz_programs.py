@@ -179,3 +179,26 @@ def test_random_float_program_matches_oracle(dim, seed):
                 assert np.array_equal(got.reshape(want.shape).view(np.uint64), want.view(np.uint64)), (dim, seed, step, st["name"], setup.boundary)
             else:
                 assert np.float64(m.scalar(st["name"])).view(np.uint64) == o.scalar(st["name"]).view(np.uint64)[0], (dim, seed, step)
+
+
+# ---- random programs through the generated C++ class on several emulated devices -------------------------------------------------
+@pytest.mark.parametrize("seed", [3, 14, 17, 21])
+def test_random_program_on_several_devices_equals_one(seed, tmp_path):
+    """Slab decomposition of arbitrary stencils (asymmetric reach of up to six rows, Open and Cyclic cuts, reduces feeding a
+    second stage): the generated class on 2 and 3 emulated devices prints what one device prints."""
+    import os
+    from tests.emu import hostclass
+    from tests.generic_driver import driver_source
+    om, setup = random_program(seed)
+    setup.local_size = (setup.local_size[0], 24)            # tall enough for three slabs of any reach
+    tag = f"fuzzdev_{seed}"
+    desc, _so = build_emulated(setup, om(), tag=tag)
+    drv = str(tmp_path / "driver.cpp")
+    with open(drv, "w") as f:
+        f.write(driver_source(desc, ["k", "k", "k"]))
+    exe = str(tmp_path / "drv")
+    hostclass.link_emulated(setup, om(), tag, drv, exe)
+    want = hostclass.run(exe)
+    assert want.strip()
+    for devices in (2, 3):
+        assert hostclass.run(exe, devices=devices) == want, devices
