@@ -94,6 +94,17 @@ def _hydro_emulated(size, steps, fast=False, prefetch=None, tag=None):
     return m, o, so
 
 
+@pytest.mark.parametrize("size", [(1, 1), (129, 5)])
+def test_hydro_ragged_and_tiny_grids_bit_identical(size):
+    """Grids narrower than the margin (3), than one vector (2 doubles) and than one CTA strip, odd widths: every array
+    including its margin cells and the CFL time step equal the oracle bit for bit (offline also (5,3) (2,3) (3,70) (260,33)
+    (4,4) (7,1) (1,9))."""
+    m, o, _so = _hydro_emulated(size, 2)
+    for n in ["density", "velocity0", "velocity1", "pressure"]:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
+    assert m.scalar("time") == o.scalar("time")[0]
+
+
 def test_hydro_register_prefetch_of_unstaged_inputs_bit_identical():
     """Tuning.direct_prefetch: inputs read at column offset 0 are loaded one row ahead at the loop top."""
     m, o, so = _hydro_emulated((70, 37), 2, prefetch=True, tag="Hydro_pf")
