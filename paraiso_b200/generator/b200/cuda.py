@@ -25,6 +25,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
+from ...annotation import CYCLIC, OPEN
 from ...om.graph import ARRAY, CPP_TYPE, SCALAR, TYPE_BYTES, OM, imm_value
 from ..plan import Plan
 from .schedule import KernelSchedule, Op, Stage
@@ -133,6 +134,11 @@ class StageEmitter:
             self.depth[m.vid] = m.depth
         self.static_of = {i.vid: i.static_idx for i in st.inputs.values()}
         self.margin_lo = tuple(plan.lower_margin) + (0,) * (3 - len(plan.lower_margin))
+        # loadIndex on an axis generated Cyclic wraps with the reference's full modulo (om_wrap_far): index shifts compose past
+        # the stencil radius and the grid may be narrower than the ghost width.  Axes generated Open keep the one-period form
+        # behind their (never taken) run-time test.
+        bnd = tuple(plan.setup.boundary) + (OPEN,) * (3 - len(plan.setup.boundary))
+        self.wrap_fn = tuple("om_wrap_far" if b == CYCLIC else "om_wrap" for b in bnd)
         self.margin_hi = tuple(plan.upper_margin) + (0,) * (3 - len(plan.upper_margin))
         self.dim3 = plan.setup.dim == 3                    # rank 3: one plane of axis 2 per blockIdx.z (schedule.lower_z)
         self.zoff_of = {i.vid: i.zoff for i in st.inputs.values()}
@@ -406,12 +412,12 @@ class StageEmitter:
                         hn = f"hix_{_m(cur[0])}_{k}"
                         if hn not in self.pre_names:
                             self.pre_names.add(hn)
-                            self.pre.append(f"const int {hn} = g.cyc_x ? om_wrap(tc + {k} + ({cur[0]}) - g.xorg, g.nx) : (tc + {k} + ({cur[0]}) - g.xorg);")
+                            self.pre.append(f"const int {hn} = g.cyc_x ? {self.wrap_fn[0]}(tc + {k} + ({cur[0]}) - g.xorg, g.nx) : (tc + {k} + ({cur[0]}) - g.xorg);")
                         lines.append(f"const int {nm} = {hn};")
                     elif ax == 1:
-                        lines.append(f"const int {nm} = g.cyc_y ? om_wrap(row + ({cur[1]}) - g.yorg + g.y0, g.ny) : (row + ({cur[1]}) - g.yorg + g.y0);")
+                        lines.append(f"const int {nm} = g.cyc_y ? {self.wrap_fn[1]}(row + ({cur[1]}) - g.yorg + g.y0, g.ny) : (row + ({cur[1]}) - g.yorg + g.y0);")
                     else:      # axis 2: the CTA's plane plus the offset lower_z gave this node
-                        lines.append(f"const int {nm} = g.cyc_z ? om_wrap(zp + ({op.zoff}) - g.zorg + g.z0, g.nz) : (zp + ({op.zoff}) - g.zorg + g.z0);")
+                        lines.append(f"const int {nm} = g.cyc_z ? {self.wrap_fn[2]}(zp + ({op.zoff}) - g.zorg + g.z0, g.nz) : (zp + ({op.zoff}) - g.zorg + g.z0);")
                 e = f"(({T}){nm})"
             elif op.kind == "LoadSize":
                 e = f"(({T}){('g.nx', 'g.ny', 'g.nz')[op.inst.arg]})"

@@ -69,7 +69,9 @@ def random_program(seed: int):
     return om, Setup(local_size=size, boundary=bnd)
 
 
-@pytest.mark.parametrize("seed", list(range(12)) + [76])   # 76: a shifted immediate is reduced (regression, see below)
+# 76: a shifted immediate is reduced (regression, see below); 1057: Shift (-3,-3) of Shift (2,-3) of loadIndex 1 on a Cyclic
+# axis of 5 rows reads row y + 6, two periods out of range (om_wrap_far: the reference's (i + n) % n, PlanTrans.hs:459-462)
+@pytest.mark.parametrize("seed", list(range(12)) + [76, 1057])
 def test_random_program_matches_oracle(seed):
     om, setup = random_program(seed)
     desc, so = build_emulated(setup, om(), tag=f"fuzz_{seed}")
