@@ -221,6 +221,9 @@ class Machine:
         if rc != 0:
             raise RuntimeError(f"{st['symbol']} failed with CUDA error {rc}")
         self.launches += 1
+        if self._narrow():
+            for o in st["outputs"]:
+                self._fill_ghosts_modular(self.alt[o])
 
     def _join_comm(self):
         """Make the compute stream wait for the ghost-row exchange that is still in flight on the side stream."""
@@ -358,8 +361,43 @@ class Machine:
         if self.gz_hi:
             a3[z1:z1 + self.gz_hi] = a3[z0:z0 + self.gz_hi]
 
+    def _narrow(self) -> bool:
+        """A Cyclic axis this rank holds whole is narrower than its two ghost zones together.  A cell then has more images
+        than the kernels' fused ghost writes produce (one per direction and axis, plus the corner), so the host redoes the
+        wrap after every launch — grids of a few cells only, never the measured path."""
+        cached = self.__dict__.get("_narrow_cached")
+        if cached is not None:
+            return cached
+        whole_y = self.nranks == 1 or self.dim3
+        self._narrow_cached = bool((self.cyc[0] and self.nx < self.gx_lo + self.gx_hi) or
+                    (self.cyc[1] and whole_y and self.nyl < self.gy_lo + self.gy_hi) or
+                    (self.dim3 and self.cyc[2] and self.nranks == 1 and self.nzl < self.gz_lo + self.gz_hi))
+        return self._narrow_cached
+
+    @staticmethod
+    def _wrap_axis(v: torch.Tensor, dim: int, org: int, n: int, g_lo: int, g_hi: int):
+        """Ghost cells of one axis <- interior cell (j mod n), for any ghost width (also wider than the interior)."""
+        if g_lo or g_hi:
+            idx = torch.remainder(torch.arange(-g_lo, n + g_hi, device=v.device), n) + org
+            v.narrow(dim, org - g_lo, g_lo + n + g_hi).copy_(v.index_select(dim, idx))
+
+    def _fill_ghosts_modular(self, a: torch.Tensor):
+        v = self._v3(a) if self.dim3 else a
+        d = 1 if self.dim3 else 0
+        if self.cyc[0]:
+            self._wrap_axis(v, d + 1, self.xorg, self.nx, self.gx_lo, self.gx_hi)
+        if self.cyc[1] and (self.nranks == 1 or self.dim3):
+            self._wrap_axis(v, d, self.yorg, self.nyl, self.gy_lo, self.gy_hi)
+        if self.dim3 and self.cyc[2] and self.nranks == 1:
+            self._wrap_axis(v, 0, self.zorg, self.nzl, self.gz_lo, self.gz_hi)
+
     def _fill_ghosts(self, a: torch.Tensor):
         """Host-initiated ghost refresh after the host wrote an array (not on the step path)."""
+        if self._narrow():
+            self._fill_ghosts_modular(a)
+            if self.nranks > 1:
+                self._exchange_rows(a)
+            return
         if self.dim3:
             a3 = self._v3(a)
             x0, x1 = self.xorg, self.xorg + self.nx

@@ -204,3 +204,44 @@ def test_random_program_on_several_devices_equals_one(seed, tmp_path):
     assert want.strip()
     for devices in (2, 3):
         assert hostclass.run(exe, devices=devices) == want, devices
+
+
+# ---- Cyclic grids narrower than their two ghost zones together (seed 1069: 130 x 5 with reach 3 + 3) ---------------------------
+def _oracle_exe(setup, om, drv, tmp_path):
+    """The generic driver against the oracle's reference-style class (header-only text of oracle/plantrans.py)."""
+    import os
+    import subprocess
+
+    from oracle import plantrans
+    from paraiso_b200.generator.plan import translate
+    hdr = tmp_path / "oracle_hdr"
+    hdr.mkdir(exist_ok=True)
+    (hdr / f"{om.name}.hpp").write_text(plantrans.emit(translate(setup, om)))
+    exe = str(tmp_path / "oracle_drv")
+    subprocess.run([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-w", "-ffp-contract=off", f"-I{hdr}", "-x", "c++", drv,
+                    "-o", exe], check=True)
+    return exe
+
+
+def test_narrow_cyclic_grid_python_host():
+    """A cell of a 5-row Cyclic axis with ghost zones of 3 + 3 rows has two images along that axis and four more in the
+    corners; the kernels' fused ghost writes produce one per direction and the corner, the host redoes the wrap."""
+    test_random_program_matches_oracle(1069)
+
+
+def test_narrow_cyclic_grid_generated_host_class_equals_reference_style_class(tmp_path):
+    import subprocess
+
+    from tests.emu import hostclass
+    from tests.generic_driver import driver_source
+    om, setup = random_program(1069)
+    assert setup.boundary == (CYCLIC, CYCLIC) and setup.local_size == (130, 5)
+    desc, _so = build_emulated(setup, om(), tag="fuzzdev_narrow")
+    assert max(desc["radius_lo"][1], desc["radius_hi"][1]) <= 5 < desc["radius_lo"][1] + desc["radius_hi"][1]
+    drv = str(tmp_path / "driver.cpp")
+    with open(drv, "w") as f:
+        f.write(driver_source(desc, ["k", "k", "k"]))
+    exe = str(tmp_path / "drv")
+    hostclass.link_emulated(setup, om(), "fuzzdev_narrow", drv, exe)
+    want = subprocess.run([_oracle_exe(setup, om(), drv, tmp_path)], capture_output=True, text=True, check=True).stdout
+    assert want.strip() and hostclass.run(exe) == want
