@@ -99,7 +99,7 @@ def arith_expr(op: Op, a: List[str]) -> str:
     raise NotImplementedError(o)
 
 
-APRON_ROWS = 16   # allocated (zero-initialised) rows the host must provide above and below every array
+APRON_ROWS = 32   # allocated (zero-initialised) rows the host must provide above and below every array
 VEC_TYPE = {("int", 4): "int4", ("float", 4): "float4", ("double", 2): "double2", ("int", 2): "int2", ("float", 2): "float2"}
 
 
@@ -167,7 +167,9 @@ class StageEmitter:
         lags = [i.lag for i in st.inputs.values()] + [0]
         lows = [i.lag - i.depth + 1 for i in st.inputs.values()] + [0]
         reach = max(st.warmup + max(0, -min(lows)), max(lags) + self.PF) + 1
-        assert reach <= APRON_ROWS, f"stage needs {reach} apron rows"
+        if reach > APRON_ROWS:
+            raise ValueError(f"stage needs {reach} apron rows, the ABI provides OM_APRON_ROWS = {APRON_ROWS}: lower "
+                             "Tuning.prefetch_rows or raise Tuning.mat_threshold (fewer shared-memory rings, shorter warm-up)")
 
     # ------------------------------------------------------------------------------------------
     def T(self, v) -> str:

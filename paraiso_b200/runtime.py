@@ -30,7 +30,7 @@ from .annotation import CYCLIC
 TORCH_TYPE = {"Int": torch.int32, "Float": torch.float32, "Double": torch.float64, "Bool": torch.bool,
               "Integer": torch.int64}
 NP_TYPE = {"Int": np.int32, "Float": np.float32, "Double": np.float64, "Bool": np.bool_, "Integer": np.int64}
-APRON = 16   # = APRON_ROWS of generator/b200/cuda.py
+APRON = 32   # = APRON_ROWS of generator/b200/cuda.py
 
 
 class OmGeom(ctypes.Structure):

@@ -64,10 +64,10 @@ def link_tsan(setup, om, tag: str, driver: str, exe: str, drop_barrier: int = No
     if apron is not None:
         with open(host_cpp) as f:
             text = f.read()
-        assert "const int APRON = 16;" in text
+        assert "const int APRON = 32;" in text
         host_cpp = os.path.join(work, f"{name}_apron{apron}.cpp")
         with open(host_cpp, "w") as f:
-            f.write(text.replace("const int APRON = 16;", f"const int APRON = {apron};"))
+            f.write(text.replace("const int APRON = 32;", f"const int APRON = {apron};"))
     r = subprocess.run(common + [f"-I{os.path.join(HERE, 'cudart')}", f"-I{d}", driver, host_cpp, obj, "-o", exe],
                        capture_output=True, text=True)
     if r.returncode != 0:

@@ -84,7 +84,7 @@ def test_kernels_stay_inside_their_allocations(case, tmp_path):
 
 
 def test_missing_apron_rows_are_reported(tmp_path):
-    """Negative control of the memory check: a host that allocates no slack rows (the ABI asks for OM_APRON_ROWS = 16)
+    """Negative control of the memory check: a host that allocates no slack rows (the ABI asks for OM_APRON_ROWS = 32)
     makes the Life kernel's pipeline fill read outside the allocation, and AddressSanitizer says so."""
     setup, om, tag, driver, steps = _asan_cases()["life"]
     exe = _need(hostclass.link_tsan(setup, om, tag, os.path.join(CPP, driver), str(tmp_path / "life_noapron"), sanitizer="address", apron=0))
