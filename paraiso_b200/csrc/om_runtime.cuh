@@ -34,6 +34,9 @@ struct OmGeom {
   int zorg, gz_lo, gz_hi, cyc_z; // device plane of interior plane 0, ghost planes, Cyclic axis 2
   int own_z0, own_z1;            // device planes this launch computes (grid z)
   int z0, nzl;                   // rank 3 with several ranks: the slab is cut along axis 2; global index of local plane 0, local planes
+  // several ranks, light stages (0 / 0 / 0 otherwise): boundary-first chunk order + in-kernel "boundary rows written" signal
+  int bfirst;                    // 1: blockIdx.y 0 computes the LAST chunk of rows, blockIdx.y c > 0 computes chunk c - 1
+  int sig_lo, sig_hi;            // a neighbour reads rows of the first / last chunk: the CTAs of that chunk signal when done
 };
 
 // Scalars (static Scalar-realm variables and reduce results) live in 8-byte device slots.
@@ -98,6 +101,41 @@ __device__ __forceinline__ void om_mbar_wait(uint64_t* bar, unsigned parity) {
   } while (!done);
 }
 #endif  // OM_EMULATED_INTRINSICS
+
+// ---- "boundary rows written" signal (slab decomposition over several GPUs) ------------------------------------------------
+// A stage launched with g.bfirst computes the chunks holding the rows its neighbours need in the first wave.  Every CTA of
+// those chunks arrives here once its rows are stored; the last one raises a flag in the scratch header that a one-thread
+// kernel on the host's communication stream (om_wait_boundary) is spinning on, so the NCCL send/recv of the ghost rows
+// starts ~one CTA duration into the launch and overlaps the rest of it — one launch per step, no separate boundary launches.
+#define OM_SIG_COUNTER 32        // word index in the scratch header: arrivals of boundary CTAs
+#define OM_SIG_FLAG 33           // ... 1 once all of them have stored their rows (reset by om_wait_boundary)
+#define OM_SIG_TIMEOUT 34        // ... 1 if om_wait_boundary ever gave up waiting (the host checks it at its sync points)
+__device__ __forceinline__ void om_signal_boundary(unsigned* hdr, unsigned nsig) {   // all threads, after a __syncthreads()
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(&hdr[OM_SIG_COUNTER], 1u);
+    if (prev == nsig - 1u) {
+      hdr[OM_SIG_COUNTER] = 0u;
+      __threadfence();
+      *((volatile unsigned*)&hdr[OM_SIG_FLAG]) = 1u;
+    }
+  }
+}
+#ifndef OM_EMULATED_INTRINSICS
+__global__ void om_wait_boundary_kernel(unsigned* hdr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  volatile unsigned* flag = (volatile unsigned*)&hdr[OM_SIG_FLAG];
+  // bounded spin (~4 s): a launch that never signals must not hang the device
+  for (long long i = 0; *flag == 0u; ++i) {
+    __nanosleep(200);
+    if (i > 20000000LL) { hdr[OM_SIG_TIMEOUT] = 1u; break; }
+  }
+  *flag = 0u;
+  __threadfence();
+}
+#else
+static void om_wait_boundary_kernel(unsigned* hdr) { if (hdr[OM_SIG_FLAG] == 0u) hdr[OM_SIG_TIMEOUT] = 1u; hdr[OM_SIG_FLAG] = 0u; }
+#endif
 
 // ---- reductions (OM/Reduce.hs:9: Max | Min | Sum) ----------------------------------------------
 struct OmSum { template <class T> __device__ __forceinline__ static T op(T a, T b) { return a + b; } };

@@ -610,7 +610,10 @@ class StageEmitter:
         E("  const int cA = (cx0 / V) * V;")
         E("  const int strip_lo = cA + blockIdx.x * W_OUT;            // first output column of this CTA")
         E("  const int tc = strip_lo - HL + tid * V;                  // first column of this thread")
-        E("  const int r0 = g.own_r0 + blockIdx.y * g.chunk_rows;")
+        E("  // several ranks (g.bfirst): the chunk with the slab's top rows runs first, then chunks 0, 1, ... — both chunks a neighbour")
+        E("  // reads from are in the first wave and signal the host's communication stream once their rows are stored")
+        E("  const int cy = g.bfirst ? (blockIdx.y == 0 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1) : (int)blockIdx.y;")
+        E("  const int r0 = g.own_r0 + cy * g.chunk_rows;")
         E("  const int r1 = min(r0 + g.chunk_rows, g.own_r1);")
         E(f"  const int jbeg = r0 - {lead};")
         if self.dim3:
@@ -649,6 +652,10 @@ class StageEmitter:
                 E(ind + f"++it; if (++bar_i == {self.NBAR}) bar_i = 0; if (++bar_w == {self.NBAR}) {{ bar_w = 0; bar_wp ^= 1; }}")
             if nb_ > 1:
                 E("    }")
+        E("  }")
+        E("  if (g.bfirst && ((g.sig_lo && cy == 0) || (g.sig_hi && cy == (int)gridDim.y - 1))) {   // this CTA's rows are what a neighbour waits for")
+        E("    __syncthreads();")
+        E("    om_signal_boundary(red_counter, gridDim.x * ((g.sig_lo ? 1u : 0u) + ((g.sig_hi && (gridDim.y > 1 || !g.sig_lo)) ? 1u : 0u)));")
         E("  }")
         L += self.emit_reduce_epilogue()
         E("}")

@@ -469,6 +469,28 @@ class Machine:
         dst.copy_(host.view(dst.shape), non_blocking=True)
         self._fill_ghosts(self.cur[i])
 
+    def set_from_device(self, name: str, src: torch.Tensor):
+        """Replace the local interior by a device tensor (stream-ordered device copy + ghost refresh)."""
+        i = self.index[name]
+        rz, ry, rx = self._box(False)
+        self._join_comm()
+        self._carry_kernel = None
+        dst = self._v3(self.cur[i])[rz, ry, rx]
+        dst.copy_(src.view(dst.shape))
+        self._fill_ghosts(self.cur[i])
+
+    def interior_into(self, name: str, dst: torch.Tensor):
+        """Stream-ordered copy of the local interior into a device tensor (no host synchronisation)."""
+        rz, ry, rx = self._box(False)
+        src = self._v3(self.cur[self.index[name]])[rz, ry, rx]
+        dst.view(src.shape).copy_(src)
+
+    def capture(self, kernel: str, calls: int = 2) -> "GraphedCalls":
+        """`calls` consecutive calls of an OM kernel captured into one CUDA graph (launches, ghost-row exchange,
+        all-reduces and stream hops included).  `calls` must be even so that the current / alternate buffers are back in
+        place after a replay.  Warm the kernel up with a few eager calls first (NCCL connections, function attributes)."""
+        return GraphedCalls(self, kernel, calls)
+
     def scalar(self, name: str):
         """Host read of a static scalar (synchronises).  With several ranks the read of a reduce-derived scalar
         that no kernel consumes is collective: every rank must call it (the all_reduce was deferred to here)."""
@@ -490,3 +512,54 @@ class Machine:
         self._join_comm()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
+
+
+class GraphedCalls:
+    """An even number of consecutive calls of one OM kernel as a CUDA graph ("whole step captured in a CUDA graph").
+
+    The reference's per-kernel driver is a serial list of subkernel calls (PlanTrans.hs:225-258); here a step is a handful of
+    launches, stream hops and NCCL operations issued by the host, and on several GPUs that issue cost (not NVLink) is what
+    separates N ranks from one.  Replaying the captured pair costs one graph launch.  The buffers swap twice per replay, so
+    the baked-in pointers stay valid; host-side bookkeeping (pending partial reduces, carried-reduce validity, the launch
+    counter) is replayed alongside."""
+
+    def __init__(self, m: Machine, kernel: str, calls: int = 2):
+        if calls < 2 or calls % 2:
+            raise ValueError("capture an even number of calls: the current / alternate buffers must be back in place")
+        if m.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        if m._narrow():
+            raise RuntimeError("narrow Cyclic grids redo their ghost wrap on the host side: not capturable")
+        self.m, self.kernel, self.calls = m, kernel, calls
+        k = m.kernels[kernel]
+        self.needs_carry = bool(k.get("carry")) and m._carry_kernel == kernel
+        m._join_comm()
+        torch.cuda.synchronize(m.device)
+        ptrs = [t.data_ptr() for t in m.cur if t is not None]
+        l0, partial0 = m.launches, dict(m._partial)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            for _ in range(calls):
+                m.call(kernel)
+            m._join_comm()
+        assert ptrs == [t.data_ptr() for t in m.cur if t is not None]
+        self.launches_per_replay = m.launches - l0
+        # the capture itself executed nothing: the machine's state is what it was, and so is the carried-reduce validity
+        m._carry_kernel = kernel if self.needs_carry else None
+        self._after = dict(partial=dict(m._partial), carry=kernel if k.get("carry") else None)
+        m.launches = l0
+        m._partial.clear()
+        m._partial.update(partial0)
+
+    def replay(self):
+        m = self.m
+        if self.needs_carry and m._carry_kernel != self.kernel:
+            # something wrote the state since the last call: the carried reduce baked into the graph's first call is stale
+            for _ in range(self.calls):
+                m.call(self.kernel)
+            return
+        m._join_comm()
+        self.graph.replay()
+        m.launches += self.launches_per_replay
+        m._partial.update(self._after["partial"])
+        m._carry_kernel = self._after["carry"]
