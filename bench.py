@@ -50,7 +50,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def config_for(workload: str, world: int, build: str = "") -> dict:
+def config_for(workload: str, world: int) -> dict:
     """`config` of a line — the same dict for both arms (ours / reference) at the same N."""
     if workload == "life":
         g = (LIFE_SIZE[0], LIFE_SIZE[1] * world)
@@ -60,12 +60,11 @@ def config_for(workload: str, world: int, build: str = "") -> dict:
     if workload == "hydro32k":
         return {"workload": "Hydro 2D Euler KH 32768x32768 double, slab-decomposed over the GPUs (examples/Hydro/HydroMain.hs, Open)",
                 "global_grid": "32768x32768", "per_gpu_grid": f"32768x{32768 // world}", "decomposition": f"slab{world}",
-                "l2": "state arrays are larger than L2 (no flush needed)", "build": build}
+                "l2": "state arrays are larger than L2 (no flush needed)"}
     g = (HYDRO_SIZE[0], HYDRO_SIZE[1] * world)
     return {"workload": "Hydro 2D Euler KH 4096x4096 double per GPU (examples/Hydro/HydroMain.hs, Open)",
             "global_grid": f"{g[0]}x{g[1]}", "per_gpu_grid": f"{HYDRO_SIZE[0]}x{HYDRO_SIZE[1]}",
-            "decomposition": f"slab{world}" if world > 1 else "single", "l2": "state arrays are larger than L2 (no flush needed)",
-            "build": build}
+            "decomposition": f"slab{world}" if world > 1 else "single", "l2": "state arrays are larger than L2 (no flush needed)"}
 
 
 BUILD_NAME = {"fast": "fast_math (FMA, MUFU-seeded div/sqrt; within 1e-12 of the reference)",
@@ -185,7 +184,7 @@ def reference_arm(args):
     line = sub("life", lv, lms, steps, warm, "i32", config_for("life", args.gpus))
     line["omp_threads"] = thr
     line["workloads"] = {"life": {"value": lv, "ms_per_step": lms},
-                         "hydro": sub("hydro", hv, hms, hsteps, hwarm, "f64", config_for("hydro", args.gpus, "reference C++ (double)"))}
+                         "hydro": sub("hydro", hv, hms, hsteps, hwarm, "f64", config_for("hydro", args.gpus))}
     print(json.dumps(line))
 
 
@@ -400,7 +399,8 @@ def main():
         achieved = m.nx * m.nyl * ALG_BYTES["life"] / (kms * 1e-3) / 1e9
         sub = {"metric": "Gcell-updates/s", "value": r["value"], "unit": "Gcell/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-               "config": dict(config_for("life", world), build="integer (bit-exact)", stepping="CUDA graph of 2 steps" if r["graph"] else "host-issued"),
+               "config": config_for("life", world), "build": "integer (bit-exact)",
+               "stepping": "CUDA graph of 2 steps" if r["graph"] else "host-issued",
                "roofline": {"bound": "hbm", "kernel": kinfo["stages"][dom]["symbol"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": measured_traffic(m, kinfo["stages"][dom]["symbol"], ""), "peak_source": peak_src,
                             "algorithmic_bytes_per_cell": ALG_BYTES["life"], "kernel_ms": kms},
@@ -487,8 +487,9 @@ def main():
         achieved = m.nx * m.nyl * ALG_BYTES["hydro"] / (kms * 1e-3) / 1e9
         sub = {"metric": "Gcell-updates/s", "value": r["value"], "unit": "Gcell/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic", "build": build,
-               "config": dict(config_for("hydro32k" if strong else "hydro", world, BUILD_NAME[build]), stepping="CUDA graph of 2 steps" if r["graph"] else "host-issued"),
+               "data": "synthetic", "build": BUILD_NAME[build],
+               "config": config_for("hydro32k" if strong else "hydro", world),
+               "stepping": "CUDA graph of 2 steps" if r["graph"] else "host-issued",
                "roofline": {"bound": "hbm", "kernel": kinfo["stages"][dom]["symbol"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": measured_traffic(m, kinfo["stages"][dom]["symbol"], "_" + build), "peak_source": peak_src,
                             "algorithmic_bytes_per_cell": ALG_BYTES["hydro"], "kernel_ms": kms,
@@ -542,6 +543,7 @@ def main():
                 torch.cuda.empty_cache()
                 same = True
                 if rank == 0:
+                  try:
                     b = hydro_machine(gsize, fast=fast, device=dev)
                     hydro_set_params(b, gsize); b.call("init")
                     for _ in range(vs):
@@ -554,6 +556,9 @@ def main():
                         same = same and ref == [int(x) for x in allsums[rk].tolist()]
                     del b
                     torch.cuda.empty_cache()
+                  except Exception as ex:      # rank-local: the other ranks are waiting in all_true below
+                    same = False
+                    checks["one_rank_32768x32768_error"] = repr(ex)[:200]
                 checks["n_ranks_equal_one_rank_32768x32768_%dsteps_checksums" % vs] = all_true(same)
         e2e = None
         if not args.no_e2e and not strong:

@@ -39,6 +39,16 @@
  * covers device planes [own_z0, own_z1) with one layer of CTAs per plane, and the host copies the ghost planes of a
  * Cyclic axis 2 after each store; with several ranks the slab is cut along axis 2 (`z0` = global index of local plane 0,
  * `nzl` local planes).  Rank-1 / rank-2 callers pass nz = 1, plane = 0, own_z0 = 0, own_z1 = 1, z0 = 0, nzl = 1.
+ *
+ * Several ranks (ABI version 3): `g->bfirst = 1` launches a stage in boundary-first chunk order — blockIdx.y 0 computes the
+ * LAST chunk of rows, blockIdx.y c > 0 chunk c - 1 — so the rows the slab's neighbours read (`sig_lo`: rows of the first
+ * chunk, `sig_hi`: rows of the last chunk) are written by the first wave of CTAs.  The last of those CTAs raises a flag in
+ * the scratch header, and
+ *     int om_<Name>_wait_boundary(void* scratch, void* stream);
+ * enqueues a one-thread kernel on `stream` (the host's high-priority communication stream) that completes when the flag is
+ * up: ncclSend / ncclRecv of the ghost rows enqueued behind it overlap the remaining waves of the same launch.  This replaces
+ * separate boundary launches; the reference has no counterpart (single device, PlanTrans.hs:318-343).  Single-rank callers
+ * pass bfirst = sig_lo = sig_hi = 0.
  */
 #pragma once
 #include "om_Life_abi.h"

@@ -372,17 +372,16 @@ def hydro_om(variant: str = "master", real: str = None) -> OM:
 
 
 def hydro_setup(size=(1024, 1024), periodic: bool = False, fast: bool = False) -> Setup:  # HydroMain.hs:290-294
-    """`fast` = Setup.fast_math.  The schedule knobs are the winners of tools/sweep_hydro.py on the B200
-    (profiles/r1_hydro_sweep.txt): the IEEE build is short of registers, so it does without the register prefetch of
-    unstaged inputs and keeps two 256-thread CTAs per SM; the fast build runs three 128-thread CTAs per SM."""
+    """`fast` = Setup.fast_math.  The schedule knobs are the winners of the sweeps on the B200 (profiles/r1_hydro_sweep.txt,
+    profiles/r2e_sweep_exact.jsonl): both builds run three 128-thread CTAs per SM."""
     from ..annotation import CYCLIC
     s = Setup(local_size=tuple(size), boundary=(CYCLIC, CYCLIC) if periodic else (OPEN, OPEN), directory="./dist/")
     s.fast_math = fast
-    if fast:
-        # 128-thread CTAs, three per SM (up to 168 registers per thread): 12.15 Gcell/s vs 11.24 with two 256-thread CTAs
-        s.tuning.threads_heavy = 128
-        s.tuning.min_blocks_heavy = 3
-        s.tuning.carry_reduces = True     # dt of the next step is reduced in this step's epilogue: +2.6 % (IEEE build: -6 %)
-    else:
-        s.tuning.direct_prefetch = False
+    # 128-thread CTAs, three per SM (up to 168 registers per thread), register prefetch of the unstaged inputs, and dt of the
+    # next step reduced in this step's epilogue.  fast build: 12.15 Gcell/s vs 11.24 with two 256-thread CTAs (round 1);
+    # bit-exact build with the branch-free IEEE-correct division (Tuning.exact_divsqrt = "newton"): the same shape wins the
+    # 48-candidate sweep of profiles/r2e_sweep_exact.jsonl (10.0 Gcell/s; two 256-thread CTAs without prefetch: 9.6)
+    s.tuning.threads_heavy = 128
+    s.tuning.min_blocks_heavy = 3
+    s.tuning.carry_reduces = True
     return s

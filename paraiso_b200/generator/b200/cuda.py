@@ -119,6 +119,10 @@ class StageEmitter:
         self.V, self.NT = V, NT
         self.fast = bool(getattr(plan.setup, "fast_math", False))
         self.tuning = plan.setup.tuning
+        self.newton = (not self.fast) and self.tuning.exact_divsqrt == "newton"   # branch-free IEEE-correct Double division / sqrt
+        self.uses_range_flag = False
+        self._ieee_scope = False      # emitting the cold clone of a scope: the compiler's own IEEE division / sqrt
+        self._guarded_ops = 0         # guarded divisions / square roots emitted by the scope() call in progress
         self.PF = self.tuning.prefetch_rows     # cp.async prefetch distance in rows
         self.HL, self.HR = _ru(st.halo_x[0], V), _ru(st.halo_x[1], V)
         self.PL, self.PR = _ru(st.pad_x[0], V), _ru(st.pad_x[1], V)
@@ -194,6 +198,11 @@ class StageEmitter:
         nm = f"outz{s}"
         self.zdefs[nm] = f"{T}* __restrict__ {nm} = out{s} + (ptrdiff_t)zp * g.plane;"
         return nm
+
+    def is_light(self) -> bool:
+        """Streaming stage: one phase, rings below 48 KB — launched in many short chunks (Tuning.chunk_rows_light); a heavy
+        stage gets one full wave of equally long CTAs."""
+        return not (len(self.st.phases) > 1 or self.smem_bytes() > 48 * 1024)
 
     def smem_bytes(self) -> int:
         tot = 0
@@ -339,7 +348,7 @@ class StageEmitter:
 
         def direct_read(v, cur, k):
             assert cur[0] == 0, "direct global reads are only scheduled for column offset 0"
-            if self.direct_pf:
+            if self.direct_pf and not self._ieee_scope:      # (the cold IEEE clone re-loads instead of keeping the prefetched row alive)
                 # software pipelining: the row this iteration needs was loaded one iteration ago (loop top), so the
                 # HBM latency overlaps a whole row of arithmetic instead of stalling the few resident warps
                 off = lag + cur[1]
@@ -431,6 +440,21 @@ class StageEmitter:
             elif op.kind == "Arith":
                 args = [val(a, cur, k) for a in op.args]
                 e = self.arith(op, args)
+                if self.newton and op.ctype == "Double" and op.inst.arg in ("Max", "Min"):
+                    e = f"{'om_fmax_std' if op.inst.arg == 'Max' else 'om_fmin_std'}({args[0]}, {args[1]})"   # the same compare + select, 3 instructions
+                if (self.newton and not self._ieee_scope and op.ctype == "Double" and op.inst.arg in ("Div", "Inv", "Sqrt")
+                        and e.count("*") == 0):
+                    self.uses_range_flag = True
+                    self._guarded_ops += 1
+                    if op.inst.arg == "Sqrt":
+                        e = f"om_sqrt_rn({args[0]}, om_slow)"
+                    else:
+                        den = args[-1]
+                        rk = ("rcp", den)
+                        if rk not in memo:     # one reciprocal refinement per distinct denominator (and cursor / lane)
+                            memo[rk] = f"rc_{len([1 for q in memo if isinstance(q, tuple) and q and q[0] == 'rcp'])}_{k}"
+                            lines.append(f"const double {memo[rk]} = om_rcp_rn_seq({den}, om_slow);")
+                        e = f"om_div_rn({'1.0' if op.inst.arg == 'Inv' else args[0]}, {den}, {memo[rk]}, om_slow)"
                 if self.fast and op.ctype == "Double" and op.inst.arg in ("Max", "Min"):
                     e = f"{'om_fmax_std' if op.inst.arg == 'Max' else 'om_fmin_std'}({args[0]}, {args[1]})"   # same result, 3 instructions
                 if self.fast and op.ctype == "Double" and op.inst.arg in ("Div", "Inv", "Sqrt") and e.count("*") == 0:
@@ -455,6 +479,45 @@ class StageEmitter:
             for k in range(V):
                 result[(t, k)] = val(t, (0, 0), k)
         return lines, result
+
+    def scope_guarded(self, targets: List[int], lag: int, tag: str = "") -> Tuple[List[str], Dict]:
+        """scope() for the bit-exact build with the branch-free division / sqrt (Tuning.exact_divsqrt = "newton"): the scope's
+        code once with om_div_rn / om_sqrt_rn, which only raise the cell's `om_slow` flag on a tiny non-zero operand, and —
+        behind ONE branch — a cold clone of the same code with the compiler's IEEE expansions (slow paths included) that
+        re-evaluates the cell when the flag is up.  The scope's results are hoisted into variables both versions assign."""
+        self._guarded_ops = 0
+        lines, res = self.scope(targets, lag)
+        if not (self.newton and self._guarded_ops):
+            return lines, res
+        if self.tuning.exact_guard != "redo":      # measurement variants: the flag only, or no guard at all (dead code to the compiler)
+            return (["bool om_slow = false;"] + lines + (["om_bad |= om_slow ? 1u : 0u;"] if self.tuning.exact_guard == "flag" else [])), res
+        self._ieee_scope = True
+        try:
+            slow_lines, slow_res = self.scope(targets, lag)
+        finally:
+            self._ieee_scope = False
+        names = {key: f"g{tag}{key[0]}_{key[1]}" for key in res}
+        out = [f"{self.T(key[0])} {nm};" for key, nm in names.items()]
+        out.append("bool om_slow = false;   // a tiny non-zero operand of a division / square root: outside the branch-free sequences' range")
+        out.append("{")
+        out += ["  " + l for l in lines]
+        out += [f"  {names[key]} = {e};" for key, e in res.items()]
+        out.append("}")
+        # the cold clone lives in a function of its own (a noinline closure that captures what it reads by value), so that it
+        # costs the hot path neither registers nor scheduling freedom: inlined, it took the flux kernel from 10.0 to 7.4 Gcell/s
+        out.append("if (om_slow) {   // (cold) this cell again with the compiler's IEEE division / sqrt: every stored bit is IEEE's either way")
+        out.append("  struct OmRedo { " + " ".join(f"{self.T(key[0])} v{n};" for n, key in enumerate(res)) + " };")
+        out.append("  auto om_redo = [=]() __attribute__((noinline)) -> OmRedo {")
+        out += ["    " + l for l in slow_lines]
+        out.append("    OmRedo r;")
+        out += [f"    r.v{n} = {slow_res[key]};" for n, key in enumerate(res)]
+        out.append("    return r;")
+        out.append("  };")
+        out.append("  const OmRedo om_r = om_redo();")
+        out += [f"  {names[key]} = om_r.v{n};" for n, key in enumerate(res)]
+        out.append("  atomicAdd(&red_counter[OM_SIG_SLOW], 1u);")
+        out.append("}")
+        return out, names
 
     # ---- whole kernel ---------------------------------------------------------------------------
     def kernel(self) -> str:
@@ -566,7 +629,7 @@ class StageEmitter:
                     early = min(st.mats[m].early for m in grp)
                     B.append(f"if (j >= r0 - {-early}) {{   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
                     B.append(f"  const int row = j + {a};")
-                    lines, res = self.scope(grp, a)
+                    lines, res = self.scope_guarded(grp, a)
                     B += ["  " + l for l in lines]
                     for m in grp:
                         so = self.slot_off(self.depth[m], a)
@@ -612,9 +675,15 @@ class StageEmitter:
         E("  const int tc = strip_lo - HL + tid * V;                  // first column of this thread")
         E("  // several ranks (g.bfirst): the chunk with the slab's top rows runs first, then chunks 0, 1, ... — both chunks a neighbour")
         E("  // reads from are in the first wave and signal the host's communication stream once their rows are stored")
-        E("  const int cy = g.bfirst ? (blockIdx.y == 0 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1) : (int)blockIdx.y;")
-        E("  const int r0 = g.own_r0 + cy * g.chunk_rows;")
-        E("  const int r1 = min(r0 + g.chunk_rows, g.own_r1);")
+        # light (streaming) stages of rank-1 / rank-2 machines understand the boundary-first chunk order; heavy stages fill the
+        # GPU with one wave of long chunks, so there is nothing to reorder (and their register budget is tight)
+        self.bfirst = self.is_light() and not self.dim3
+        cy = "(g.bfirst ? (blockIdx.y == 0 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1) : (int)blockIdx.y)" if self.bfirst else "(int)blockIdx.y"
+        E("  // chunk c of gridDim.y covers rows own_r0 + [c, c + 1) * nrows / gridDim.y: heights differ by at most one row, whatever the count")
+        E("  // (32-bit unsigned arithmetic: the host keeps (chunks + 1) * rows below 2^32)")
+        E(f"  const unsigned cy_rows = (unsigned){cy} * (unsigned)(g.own_r1 - g.own_r0);")
+        E("  const int r0 = g.own_r0 + (int)(cy_rows / gridDim.y);")
+        E("  const int r1 = g.own_r0 + (int)((cy_rows + (unsigned)(g.own_r1 - g.own_r0)) / gridDim.y);")
         E(f"  const int jbeg = r0 - {lead};")
         if self.dim3:
             E(f"  const int zp = g.own_z0 + blockIdx.z * {st.zplanes};   // this CTA's (first) plane of axis 2 (device plane index)")
@@ -630,6 +699,8 @@ class StageEmitter:
             T = self.T(v)
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
+        if self.uses_range_flag:
+            E("  unsigned om_bad = 0u;   // sticky: this thread stored a NaN / Inf / denormal (om_div_rn / om_sqrt_rn are IEEE-correct for normal operands)")
         for (d, c), nm in sorted(self.slotvars.items()):
             E(f"  int {nm} = ((((jbeg + {c}) % {d}) + {d}) % {d}) * RW;")
         if self.window:
@@ -653,10 +724,14 @@ class StageEmitter:
             if nb_ > 1:
                 E("    }")
         E("  }")
-        E("  if (g.bfirst && ((g.sig_lo && cy == 0) || (g.sig_hi && cy == (int)gridDim.y - 1))) {   // this CTA's rows are what a neighbour waits for")
-        E("    __syncthreads();")
-        E("    om_signal_boundary(red_counter, gridDim.x * ((g.sig_lo ? 1u : 0u) + ((g.sig_hi && (gridDim.y > 1 || !g.sig_lo)) ? 1u : 0u)));")
-        E("  }")
+        if self.uses_range_flag:
+            E("  if (om_bad) red_counter[OM_SIG_RANGE] = 1u;   // the host raises at its next synchronisation point")
+        if self.bfirst:
+            E("  // (block indices are re-read here instead of being kept in registers across the row loop)")
+            E("  if (g.bfirst && ((g.sig_lo && blockIdx.y == 1u % gridDim.y) || (g.sig_hi && blockIdx.y == 0u))) {   // this CTA's rows are what a neighbour waits for")
+            E("    __syncthreads();")
+            E("    om_signal_boundary(red_counter, gridDim.x * ((g.sig_lo ? 1u : 0u) + ((g.sig_hi && (gridDim.y > 1 || !g.sig_lo)) ? 1u : 0u)));")
+            E("  }")
         L += self.emit_reduce_epilogue()
         E("}")
         return "\n".join(L)
@@ -716,7 +791,7 @@ class StageEmitter:
         P("const bool edge_any = edge_x || edge_y;   // this CTA writes cells that have a ghost copy")
         B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
         B.append(f"  const int row = {row_expr};")
-        lines, res = self.scope(targets, 0)
+        lines, res = self.scope_guarded(targets, 0)
         B += ["  " + l for l in lines]
         need_gmy = False
         for zo in sorted({zo_ for (_v, zo_) in entries if zo_ > 0}):
@@ -742,6 +817,11 @@ class StageEmitter:
                     B.append(f"  const {T} {oname(v, zo, k)} = ({' && '.join(conds)}) ? {res[(v, k)]} : ({T})0;")
                 else:
                     B.append(f"  const {T} {oname(v, zo, k)} = {res[(v, k)]};")
+        if self.uses_range_flag:      # the state guard of the bit-exact build: only cells this thread really stores count
+            for (s_, v_) in st.store_targets:
+                if self.ops[v_].ctype == "Double":
+                    B.append("  if (li_any) om_bad |= " + " | ".join(
+                        f"((tc + {k} >= out_lo && tc + {k} < out_hi) ? om_state_bad({oname(v_, splane(s_, v_), k)}) : 0u)" for k in range(V)) + ";")
         if need_gmy:
             idx = B.index(f"  const int row = {row_expr};")
             B.insert(idx + 1, f"  const int gmy = row - g.yorg + g.y0 + {mly}; const int memy = g.ny + {mly + mhy};   // row in the reference memory box")
@@ -804,7 +884,7 @@ class StageEmitter:
         if st.carried:
             # the level-0 reduce of the NEXT call of this kernel, evaluated on the values just stored (schedule.find_carry)
             B.append("  {   // carried reduce: next call's level-0 stage becomes an 8-byte copy")
-            lines, res = self.scope([v for (v, _o, _k) in st.carried], 0)
+            lines, res = self.scope_guarded([v for (v, _o, _k) in st.carried], 0, tag="c")
             B += ["    " + l for l in lines]
             for (v, rop, slot) in st.carried:
                 accumulate(v, rop, slot, [res[(v, k)] for k in range(V)], "    ")
@@ -862,7 +942,7 @@ class StageEmitter:
         L.append(f"  const int strips = (cx1 - cA + {self.W_OUT} - 1) / {self.W_OUT};")
         L.append("  const int nrows = g->own_r1 - g->own_r0;")
         L.append("  if (nrows <= 0 || strips <= 0) return 0;")
-        L.append("  const int chunks = (nrows + g->chunk_rows - 1) / g->chunk_rows;")
+        L.append("  const int chunks = g->nchunks > 0 ? (g->nchunks < nrows ? g->nchunks : nrows) : (nrows + g->chunk_rows - 1) / g->chunk_rows;")
         L.append("  static bool attr_set[64] = {};   // function attributes are per device")
         L.append("  int dev = 0; cudaGetDevice(&dev);")
         L.append(f"  if (dev >= 64 || !attr_set[dev]) {{ cudaError_t e = cudaFuncSetAttribute({self.name}_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, {max(smem, 1)}); if (e != cudaSuccess) return (int)e; if (dev < 64) attr_set[dev] = true; }}")

@@ -68,8 +68,11 @@ def describe(om: OM, plan: Plan, schedules: List[KernelSchedule], emitters) -> d
                         [dict(op=rop, slot=slot, type=ks.ops[v].ctype, deferred=False, stored_to=[], carried=True)
                          for (v, rop, slot) in st.carried],
                 rings=len(em.depth), phases=len(st.phases), warmup=st.warmup,
+                # boundary-first chunk order + in-kernel "boundary rows written" signal (several ranks; rank-1 / rank-2 machines)
+                bfirst=bool(getattr(em, "bfirst", False)),
                 mat_candidates=[dict(c, kernel=ks.name) for c in st.mat_candidates],
                 chunk_rows=(0 if (len(st.phases) > 1 or em.smem_bytes() > 48 * 1024) else setup.tuning.chunk_rows_light)))
+            assert not stages[-1]["bfirst"] or stages[-1]["chunk_rows"] > 0
         kernels.append(dict(
             name=ks.name, stages=stages,
             scalars=(f"om_{om.name}_{ks.name}_scalars" if ks.scalar_stores else None),
@@ -122,7 +125,13 @@ def generate(setup: Setup, om0: OM, vnt: Dict[Tuple[str, int], Tuple[int, int]] 
             cu.append(sc)
             cu.append("")
     desc = describe(om, plan, schedules, emitters)
-    cu.append(f'extern "C" int om_{om.name}_abi_version(void) {{ return 2; }}')
+    cu.append("// one thread on the host's communication stream: returns once the boundary CTAs of a g.bfirst launch have stored their rows")
+    cu.append(f'extern "C" int om_{om.name}_wait_boundary(void* scratch, void* stream) {{')
+    cu.append("  OM_LAUNCH(om_wait_boundary_kernel, dim3(1, 1), 32, 0, (cudaStream_t)stream, (unsigned*)scratch);")
+    cu.append("  OM_CUDA_CHECK_LAUNCH();")
+    cu.append("  return 0;")
+    cu.append("}")
+    cu.append(f'extern "C" int om_{om.name}_abi_version(void) {{ return 3; }}')
     with open(os.path.join(CSRC, "om_runtime.cuh")) as f:
         runtime = f.read()
     files = [(f"{om.name}_kernels.cu", "\n".join(cu) + "\n"),

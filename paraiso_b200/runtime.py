@@ -39,7 +39,25 @@ class OmGeom(ctypes.Structure):
         "nx", "ny", "pitch", "rows", "xorg", "yorg", "y0", "nyl",
         "gx_lo", "gx_hi", "gy_lo", "gy_hi", "cyc_x", "cyc_y", "wrap_y_local",
         "own_r0", "own_r1", "chunk_rows", "red_accumulate",
-        "nz", "plane", "zorg", "gz_lo", "gz_hi", "cyc_z", "own_z0", "own_z1", "z0", "nzl")]
+        "nz", "plane", "zorg", "gz_lo", "gz_hi", "cyc_z", "own_z0", "own_z1", "z0", "nzl",
+        "bfirst", "sig_lo", "sig_hi", "nchunks")]
+
+
+_HP_GROUP: Dict[int, object] = {}
+
+
+def high_priority_group():
+    """One NCCL process group over all ranks whose internal streams are high-priority: the ghost-row send/recv and the
+    scalar all-reduces must get SM slots while a stage kernel still has CTAs waiting to be scheduled."""
+    import torch.distributed as dist
+    key = dist.get_world_size()
+    if key not in _HP_GROUP:
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            _HP_GROUP[key] = dist.new_group(backend="nccl", pg_options=opts)
+        except Exception:
+            _HP_GROUP[key] = None      # the default group works too, at default priority
+    return _HP_GROUP[key]
 
 
 def _ru(x, m):
@@ -64,7 +82,7 @@ class Machine:
             raise RuntimeError("paraiso_b200 machines run on CUDA devices only (no CPU fallback)")
         self.emulated = _emulated
         self.lib = ctypes.CDLL(lib_path)   # raises OSError if the extension is missing
-        if getattr(self.lib, f"om_{self.name}_abi_version")() != 2:
+        if getattr(self.lib, f"om_{self.name}_abi_version")() != 3:
             raise RuntimeError("ABI version mismatch")
         self.rank, self.nranks, self.group = rank, nranks, group
         size = list(size) if size is not None else list(desc["local_size"])
@@ -149,12 +167,21 @@ class Machine:
                 f.restype = ctypes.c_int
                 self._fn[k["scalars"]] = f
         self.launches = 0
+        self.wave_round = True       # light stages: round the chunk count to whole waves of resident CTAs (see _geom)
+        self.early_exchanges = 0     # stage launches whose ghost-row exchange was triggered by the in-kernel boundary signal
         self._geom_cache: Dict[str, OmGeom] = {}
         self._partial: Dict[int, dict] = {}     # static scalar index -> pending all_reduce description
         self.overlap = overlap
         self._carry_kernel: Optional[str] = None   # kernel whose carried reduces are valid for its next call
         self._comm_event = None
-        self._comm_stream = torch.cuda.Stream(self.device) if (self.device.type == "cuda" and nranks > 1) else None
+        self._comm_stream = torch.cuda.Stream(self.device, priority=-1) if (self.device.type == "cuda" and nranks > 1) else None
+        if self._comm_stream is not None and group is None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend() == "nccl" and dist.get_world_size() == nranks:
+                self.group = high_priority_group()
+        self._wait_boundary = getattr(self.lib, f"om_{self.name}_wait_boundary")
+        self._wait_boundary.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        self._wait_boundary.restype = ctypes.c_int
 
     # ---- reference size accessors (PlanTrans.hs:160-215) ------------------------------------
     def om_size(self, k=None):
@@ -178,12 +205,12 @@ class Machine:
             return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return ctypes.c_void_p(0)
 
-    def _geom(self, st: dict, rows=None, accumulate: bool = False) -> OmGeom:
-        """Launch geometry of a stage over the rank's owned rows, or over the sub-range `rows` of them."""
-        key = (st["symbol"], rows, accumulate)
-        g = self._geom_cache.get(key)
-        if g is not None:
-            return g
+    def _geom(self, st: dict, rows=None, accumulate: bool = False, bfirst: bool = False) -> Optional[OmGeom]:
+        """Launch geometry of a stage over the rank's owned rows, or over the sub-range `rows` of them.  `bfirst`: boundary-first
+        chunk order with the in-kernel signal (None when the chunks do not hold a neighbour's rows whole)."""
+        key = (st["symbol"], rows, accumulate, bfirst)
+        if key in self._geom_cache:
+            return self._geom_cache[key]
         r0, r1 = rows if rows is not None else (self.own_r0, self.own_r1)
         nrows = r1 - r0
         strips = max(1, -(-(self.cx1 - (self.cx0 // st["V"]) * st["V"]) // st["w_out"]))
@@ -191,13 +218,25 @@ class Machine:
         if occ <= 0:
             raise RuntimeError(f"{st['symbol']}: occupancy query failed ({occ})")
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 4
+        layers = self.own_z1 - self.own_z0
         if st.get("chunk_rows", 0) <= 0:
             # heavy (shared-memory) stages: one full wave of equally long CTAs
             chunks = max(1, min((sms * occ) // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
         else:
             # light streaming stages: short chunks (Tuning.chunk_rows_light, measured in profiles/r1_life_sweep.txt)
-            # keep the set of concurrently streamed rows compact and balance the tail; warm-up rows are L2 hits
+            # keep the set of concurrently streamed rows compact; warm-up rows are L2 hits.  The count is then rounded to
+            # whole waves of resident CTAs (sms * occ) when that moves it by less than 8 %: a last wave that is 3/4 full
+            # costs as much as a full one (Life 16384^2: 656 chunks = 15.76 waves -> 666 chunks = 16.0 waves)
             chunks = max(1, nrows // st["chunk_rows"])
+            wave = sms * occ
+            k = max(1, round(strips * chunks * layers / wave))
+            whole = (k * wave) // (strips * layers)
+            if self.wave_round and whole >= 1 and abs(whole - chunks) <= 0.08 * chunks:
+                chunks = whole
+        # the reduction scratch holds one partial per CTA: very large slabs get fewer, taller chunks instead of more CTAs
+        if strips * chunks * layers > self.max_blocks and strips * layers <= self.max_blocks:
+            chunks = self.max_blocks // (strips * layers)
+        chunks = max(1, min(chunks, max(nrows, 1), (1 << 32) // max(nrows, 1) - 2))      # (32-bit row arithmetic in the kernels)
         chunk_rows = -(-max(nrows, 1) // chunks)
         g = OmGeom(nx=self.nx, ny=self.ny, pitch=self.pitch, rows=self.rows, xorg=self.xorg, yorg=self.yorg,
                    y0=self.y0, nyl=self.nyl, gx_lo=self.gx_lo, gx_hi=self.gx_hi, gy_lo=self.gy_lo, gy_hi=self.gy_hi,
@@ -205,15 +244,28 @@ class Machine:
                    wrap_y_local=int(self.cyc[1] and (self.nranks == 1 or self.dim3)),
                    own_r0=r0, own_r1=r1, chunk_rows=max(1, chunk_rows), red_accumulate=int(accumulate),
                    nz=self.nz, plane=(self.rows * self.pitch if self.dim3 else 0), zorg=self.zorg, gz_lo=self.gz_lo,
-                   gz_hi=self.gz_hi, cyc_z=int(self.cyc[2]), own_z0=self.own_z0, own_z1=self.own_z1, z0=self.z0, nzl=self.nzl)
-        if strips * (-(-nrows // max(1, chunk_rows))) * (self.own_z1 - self.own_z0) > self.max_blocks:
+                   gz_hi=self.gz_hi, cyc_z=int(self.cyc[2]), own_z0=self.own_z0, own_z1=self.own_z1, z0=self.z0, nzl=self.nzl,
+                   nchunks=chunks)
+        if strips * chunks * layers > self.max_blocks:
             raise ValueError("grid too large for the reduction scratch")
+        if bfirst:
+            has_up = self.cyc[1] or self.rank < self.nranks - 1
+            has_down = self.cyc[1] or self.rank > 0
+            nch, shortest = chunks, nrows // chunks
+            # the rows a neighbour reads must lie inside the first / the last chunk
+            if nch < 2 or shortest < max(self.gy_hi, self.gy_lo) or not st.get("bfirst"):
+                self._geom_cache[key] = None
+                return None
+            g.bfirst, g.sig_lo, g.sig_hi = 1, int(has_down and self.gy_hi > 0), int(has_up and self.gy_lo > 0)
+            if not (g.sig_lo or g.sig_hi):
+                self._geom_cache[key] = None
+                return None
         self._geom_cache[key] = g
         return g
 
     # ---- kernels ------------------------------------------------------------------------------
-    def _launch(self, st: dict, stream, rows=None, accumulate=False):
-        g = self._geom(st, rows, accumulate)
+    def _launch(self, st: dict, stream, rows=None, accumulate=False, bfirst=False):
+        g = self._geom(st, rows, accumulate, bfirst)
         if g.own_r1 <= g.own_r0:
             return
         rc = self._fn[st["symbol"]](ctypes.byref(g), self._ptr_cur, self._ptr_alt, self.sc.data_ptr(),
@@ -232,48 +284,71 @@ class Machine:
             self._comm_event = None
 
     def call(self, kernel: str):
-        """Run one OM kernel (`init`, `proceed`, ...) — the emitted member function of that name."""
+        """Run one OM kernel (`init`, `proceed`, ...) — the emitted member function of that name.
+
+        Several ranks: the stage that writes the kernel's array stores is followed by the ghost-row exchange of what it
+        wrote, on the high-priority communication stream.  A light (streaming) stage is launched ONCE in boundary-first
+        chunk order: the CTAs of the first wave compute the rows the neighbours need and raise a flag, a one-thread kernel
+        on the communication stream waits for it, and the NCCL send/recv overlaps the remaining waves of the same launch.
+        A heavy stage fills the GPU with one wave of CTAs, so its exchange starts when the launch ends — concurrently
+        with the all-reduce of its reduce results on the compute stream.  The next kernel call waits for the exchange."""
         k = self.kernels[kernel]
         stream = self._stream()
         self._join_comm()
         stores = k["array_stores"]
-        overlapped = False
+        cuda = self.device.type == "cuda"
         # carried reduces (schedule.find_carry): the previous call of this same kernel already reduced the arrays it
         # stored, and nothing has written them (or the scalars involved) since -> the level-0 stage is an 8-byte copy
         carry = k.get("carry")
         use_carry = bool(carry) and self._carry_kernel == kernel
         self._carry_kernel = None
+        exchanged = False
         for si, st in enumerate(k["stages"]):
             if use_carry and si == carry["skip_stage"]:
                 for (slot, cslot) in carry["pairs"]:
                     self.sc[slot:slot + 1].copy_(self.sc[cslot:cslot + 1])
                 continue
-            last_storing = self.nranks > 1 and stores and sorted(st["outputs"]) == sorted(stores)
-            # (light streaming stages only: for a heavy stage the two boundary launches pay the full pipeline
-            #  warm-up for a handful of rows, which costs more than the ~20 us exchange they would hide)
-            if (last_storing and self.device.type == "cuda" and self.overlap and st.get("chunk_rows", 0) > 0
-                    and not self.dim3 and self.nyl >= 4 * max(self.gy_lo, self.gy_hi, 1)):
-                # boundary rows first, then their exchange on a side stream (NCCL send/recv) while the interior
-                # of the slab is computed on the compute stream
-                lo_rows = (self.own_r0, self.yorg + self.gy_hi)                       # rows the lower neighbour needs
-                hi_rows = (self.yorg + self.nyl - self.gy_lo, self.own_r1)           # rows the upper neighbour needs
-                first = True
-                for rng in (lo_rows, hi_rows):
-                    if rng[1] > rng[0]:
-                        self._launch(st, stream, rng, accumulate=not first)
-                        first = False
+            last_storing = self.nranks > 1 and stores and sorted(st["outputs"]) == sorted(stores) and not self._narrow()
+            early = (last_storing and self.overlap and st.get("chunk_rows", 0) > 0 and not self.dim3
+                     and self._geom(st, bfirst=True) is not None)
+            if early and cuda:
+                # the communication stream is ordered after everything enqueued BEFORE the launch, not after the launch itself
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(self.device))
+                self._launch(st, stream, bfirst=True)
                 with torch.cuda.stream(self._comm_stream):
                     self._comm_stream.wait_event(ev)
-                    for s_ in stores:
-                        self._exchange_rows(self.alt[s_])          # alt becomes cur at the swap below
+                    rc = self._wait_boundary(self.scratch.data_ptr(), ctypes.c_void_p(self._comm_stream.cuda_stream))
+                    if rc != 0:
+                        raise RuntimeError(f"om_{self.name}_wait_boundary failed with CUDA error {rc}")
+                    self.launches += 1
+                    self._exchange_rows([self.alt[s_] for s_ in stores])       # alt becomes cur at the swap below
                     self._comm_event = torch.cuda.Event()
                     self._comm_event.record(self._comm_stream)
-                self._launch(st, stream, (max(lo_rows[1], lo_rows[0]), hi_rows[0]), accumulate=not first)
-                overlapped = True
+                self.early_exchanges += 1
+                exchanged = True
+            elif early:      # emulated kernels (tests): same launch geometry, everything in order
+                self._launch(st, stream, bfirst=True)
+                self._wait_boundary(self.scratch.data_ptr(), None)
+                if int(self.scratch[136:140].view(torch.int32)[0]) != 0:
+                    raise RuntimeError("the boundary CTAs did not signal")
+                self._exchange_rows([self.alt[s_] for s_ in stores])
+                self.early_exchanges += 1
+                exchanged = True
             else:
                 self._launch(st, stream)
+                if last_storing:
+                    if cuda:
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(self.device))
+                        with torch.cuda.stream(self._comm_stream):
+                            self._comm_stream.wait_event(ev)
+                            self._exchange_rows([self.alt[s_] for s_ in stores])
+                            self._comm_event = torch.cuda.Event()
+                            self._comm_event.record(self._comm_stream)
+                    else:
+                        self._exchange_rows([self.alt[s_] for s_ in stores])
+                    exchanged = True
             if self.nranks > 1:
                 for r in st["reduces"]:
                     if r.get("deferred"):
@@ -294,9 +369,8 @@ class Machine:
             if self.dim3 and self.cyc[2] and self.nranks == 1:
                 self._fill_z_ghosts(self.cur[s])     # whole planes (their x / y ghost cells were written by the kernel)
         self._refresh_ptrs()
-        if self.nranks > 1 and not overlapped:
-            for s in stores:
-                self._exchange_rows(self.cur[s])
+        if self.nranks > 1 and stores and not exchanged:
+            self._exchange_rows([self.cur[s] for s in stores])
         if carry:
             self._carry_kernel = kernel
 
@@ -323,27 +397,31 @@ class Machine:
         view = self.sc[r["slot"]:r["slot"] + 1].view(TORCH_TYPE[r["type"]])[:1]
         dist.all_reduce(view, op=op, group=self.group)   # 4-byte types reduce the low half of the slot; the rest stays zero
 
-    def _exchange_rows(self, a: torch.Tensor):
-        """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too).  Rank-3 machines are cut
-        along axis 2: whole ghost planes travel (their x / y ghost cells included)."""
+    def _exchange_rows(self, arrays):
+        """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too), for one array or a list
+        of arrays in ONE NCCL group (one communication kernel per exchange).  Rank-3 machines are cut along axis 2:
+        whole ghost planes travel (their x / y ghost cells included)."""
         import torch.distributed as dist
+        if isinstance(arrays, torch.Tensor):
+            arrays = [arrays]
         n, r = self.nranks, self.rank
         up, down = (r + 1) % n, (r - 1) % n
-        if self.dim3:
-            a, g_lo, g_hi, y0, y1, cyc = self._v3(a), self.gz_lo, self.gz_hi, self.zorg, self.zorg + self.nzl, self.cyc[2]
-        else:
-            g_lo, g_hi, y0, y1, cyc = self.gy_lo, self.gy_hi, self.yorg, self.yorg + self.nyl, self.cyc[1]
-        has_up = cyc or r < n - 1
-        has_down = cyc or r > 0
         ops = []
-        if g_lo and has_up:     # my top interior rows are the upper neighbour's lower ghost rows
-            ops.append(dist.P2POp(dist.isend, a[y1 - g_lo:y1], up, group=self.group))
-        if g_hi and has_down:   # my bottom interior rows are the lower neighbour's upper ghost rows
-            ops.append(dist.P2POp(dist.isend, a[y0:y0 + g_hi], down, group=self.group))
-        if g_lo and has_down:
-            ops.append(dist.P2POp(dist.irecv, a[0:g_lo], down, group=self.group))
-        if g_hi and has_up:
-            ops.append(dist.P2POp(dist.irecv, a[y1:y1 + g_hi], up, group=self.group))
+        for a in arrays:
+            if self.dim3:
+                a, g_lo, g_hi, y0, y1, cyc = self._v3(a), self.gz_lo, self.gz_hi, self.zorg, self.zorg + self.nzl, self.cyc[2]
+            else:
+                g_lo, g_hi, y0, y1, cyc = self.gy_lo, self.gy_hi, self.yorg, self.yorg + self.nyl, self.cyc[1]
+            has_up = cyc or r < n - 1
+            has_down = cyc or r > 0
+            if g_lo and has_up:     # my top interior rows are the upper neighbour's lower ghost rows
+                ops.append(dist.P2POp(dist.isend, a[y1 - g_lo:y1], up, group=self.group))
+            if g_hi and has_down:   # my bottom interior rows are the lower neighbour's upper ghost rows
+                ops.append(dist.P2POp(dist.isend, a[y0:y0 + g_hi], down, group=self.group))
+            if g_lo and has_down:
+                ops.append(dist.P2POp(dist.irecv, a[0:g_lo], down, group=self.group))
+            if g_hi and has_up:
+                ops.append(dist.P2POp(dist.irecv, a[y1:y1 + g_hi], up, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -440,6 +518,21 @@ class Machine:
         return (slice(self.zorg, self.zorg + self.nzl), slice(self.yorg, self.yorg + self.nyl),
                 slice(self.xorg, self.xorg + self.nx))
 
+    def _check_flags(self):
+        """Sticky error words of the scratch header (om_runtime.cuh), read where the host synchronises anyway."""
+        w = self.scratch[128:144].view(torch.int32).cpu().numpy()
+        if w[2]:
+            raise RuntimeError(f"{self.name}: a boundary-first launch never signalled its boundary rows (om_wait_boundary timed out)")
+        if w[3]:
+            raise RuntimeError(f"{self.name}: a stage of the bit-exact build stored a NaN, Inf or denormal value.  Its branch-free division / "
+                               "square root are IEEE-correct for normal operands only, so from here on the state may differ from the "
+                               "reference's — rebuild with Tuning.exact_divsqrt = 'ieee' (the compiler's expansion with slow paths)")
+
+    def slow_path_cells(self) -> int:
+        """Cells the bit-exact build re-evaluated with the compiler's IEEE division / sqrt so far (tiny non-zero operands;
+        diagnostic counter in the scratch header, OM_SIG_SLOW)."""
+        return int(self.scratch[144:148].view(torch.int32).cpu().numpy()[0])
+
     def get(self, name: str, with_margin: bool = False) -> np.ndarray:
         """Local slab of a static Array as [i1, i0] (axis 0 fastest), optionally with the margins
         of the reference's memory box that this rank owns; synchronises with the device."""
@@ -447,6 +540,7 @@ class Machine:
         rz, ry, rx = self._box(with_margin)
         self._join_comm()
         out = self._v3(self.cur[i])[rz, ry, rx].contiguous().cpu().numpy()
+        self._check_flags()
         return out if self.dim3 else out[0]
 
     def set(self, name: str, values: np.ndarray, with_margin: bool = False):
@@ -499,6 +593,7 @@ class Machine:
             r = self._partial.pop(self.index[name])
             self._allreduce_slot(dict(r, slot=self.index[name]))
         v = self.sc[self.index[name]:self.index[name] + 1].cpu().numpy()
+        self._check_flags()
         return v.view(NP_TYPE[s["type"]])[0]
 
     def set_scalar(self, name: str, value):
@@ -512,6 +607,7 @@ class Machine:
         self._join_comm()
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
+        self._check_flags()
 
 
 class GraphedCalls:

@@ -246,10 +246,52 @@ def genetic_search(base: Tuning, space: Dict[str, Iterable], genes, evaluate: Ca
 
 def gpu_evaluator(make_setup: Callable[[], Setup], make_om: Callable, size, kernel: str = "proceed",
                   prepare: Callable[[Machine], None] = None, fmad: bool = False, steps: int = 10,
-                  gate: Callable[[Machine], bool] = None) -> Callable[[Tuning], float]:
-    """evaluate() for genetic_search: generate + nvcc + time one individual on the GPU; inf if it fails or `gate` rejects it."""
+                  gate: dict = None, log: Callable[[dict], None] = None) -> Callable[[Tuning], float]:
+    """evaluate() for genetic_search: generate + nvcc + time one individual on the GPU; inf if it fails to build or run,
+    or if the sanity gate rejects it.
+
+    `gate` = dict(size, steps, arrays={name: expected ndarray of the local interior}, scalars={name: expected value},
+    prepare=callable(machine) or None, rtol=0.0): before an individual is timed it is run for gate["steps"] calls of
+    `kernel` on a gate["size"] grid and must reproduce the expected state — bit for bit with rtol = 0 (every schedule of
+    a bit-exact build evaluates the same SSA DAG), within rtol for fast_math builds.  This is the role of `isWorking` in
+    the reference's benchmark (examples-old/GA/main-kh.cu:20-61,96-102: a wrong individual scores zero)."""
+    import numpy as np
+
+    def passes(t: Tuning) -> bool:
+        setup = make_setup()
+        setup.tuning = t
+        desc, so = build_machine(setup, make_om(), tag=f"tune_{make_om().name}_{tag_of(t)}", fmad=fmad)
+        m = Machine(desc, so, size=gate["size"])
+        (gate.get("prepare") or prepare)(m)
+        for _ in range(gate["steps"]):
+            m.call(kernel)
+        rtol = gate.get("rtol", 0.0)
+        for n, want in gate["arrays"].items():
+            got = m.get(n)
+            if rtol == 0.0:
+                if not np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)):
+                    return False
+            elif not np.max(np.abs(got - want)) <= rtol * max(float(np.max(np.abs(want))), 1e-300):
+                return False
+        for n, want in gate.get("scalars", {}).items():
+            got = m.scalar(n)
+            if (got != want) if rtol == 0.0 else (abs(got - want) > rtol * abs(want)):
+                return False
+        return True
+
     def evaluate(t: Tuning) -> float:
+        try:
+            if gate is not None and not passes(t):
+                if log:
+                    log(dict(tuning=dataclasses.asdict(t), rejected="sanity gate"))
+                return float("inf")
+        except Exception as e:
+            if log:
+                log(dict(tuning=dataclasses.asdict(t), error=repr(e)[:300]))
+            return float("inf")
         r = grid_search(make_setup, make_om, [t], size, kernel=kernel, prepare=prepare, fmad=fmad, steps=steps)[0]
+        if log:
+            log(r)
         if "ms" not in r:
             return float("inf")
         return r["ms"]

@@ -29,5 +29,6 @@ int main(int argc, char** argv) {
     }
   printf("%d %d %d %llu %llu\n", W, H, sim.generation(), sum, hash);
   printf("population %d\n", sim.population());
+  if (getenv("OM_PRINT_EARLY")) fprintf(stderr, "early %ld\n", sim.om_early_exchanges());
   return 0;
 }

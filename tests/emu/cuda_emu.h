@@ -72,6 +72,7 @@ static EmuBlock* emu_block;
 static inline void __syncthreads() { emu_block->bar->arrive_and_wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -46,6 +46,19 @@ def main():
             }
     with open(os.path.join(HERE, "hydro_exampled.json"), "w") as f:
         json.dump(out, f, indent=1)
+    # every 8th interior cell of every state array after 3 and 10 steps (float32): lets a DIFFERENT transcription of the
+    # program (master's HydroMain.hs, float) be compared with the reference's compiled output within the north-star's 1e-5
+    h = RefHydro(openmp=True)
+    h.setup_kh()
+    h.init()
+    samples = {}
+    for t in range(1, 11):
+        h.proceed()
+        if t in (3, 10):
+            for n in names:
+                samples[f"{n}_step{t}"] = h.array(n)[3:-3, 3:-3][::8, ::8].copy()
+            samples[f"time_step{t}"] = h.scalar("time").copy()
+    np.savez_compressed(os.path.join(HERE, "hydro_exampled_samples.npz"), **samples)
     print("wrote", os.listdir(HERE))
 
 

@@ -26,6 +26,28 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "Life 16384x16384" in line["config"]["workload"] and line["dtype"] == "i32"
+    assert line["warmup"] == 1      # the driver's K / W are honoured (same_steps), on the full 16384^2 grid (same_config)
+    assert line["config"]["global_grid"] == "16384x16384" and "16384x16384" in line["cpu_baseline"]["sample"]
+    hyd = line["workloads"]["hydro"]
+    assert hyd["value"] > 0 and hyd["dtype"] == "f64" and "1024x1024" in hyd["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_forces_the_openmp_thread_count():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm must still use every core it may run on and
+    report the count OpenMP really uses."""
+    r = _bench("--impl", "reference", "--steps", "1", "--warmup", "0", env={"OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.strip().split("\n") if l.startswith("{")][0])
+    want = len(os.sched_getaffinity(0))
+    assert line["omp_threads"] == want == line["cpu_baseline"]["cores"]
+
+
+def test_config_is_the_same_dict_for_both_arms():
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (1, 2, 8):
+        assert bench.config_for("life", n)["global_grid"] == f"16384x{16384 * n}"
+        assert bench.config_for("hydro32k", max(n, 2))["global_grid"] == "32768x32768"
 
 
 def test_reference_arm_other_ranks_print_nothing():

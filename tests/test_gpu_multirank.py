@@ -31,22 +31,33 @@ def _worker(rank, world, port, which, size, steps, ret):
         for _ in range(steps):
             m.call("proceed")
         ret[rank] = (m.z0, m.get("u"), float(m.scalar("peak")))
-    elif which == "life":
+    elif which in ("life", "life_graph"):
         m = life_machine(size, device=dev, rank=rank, nranks=world)
         m.call("init")
         m.set("cell", life_seed(size[0], m.y0, m.nyl, nx_global=size[0]))
-        for _ in range(steps):
-            m.call("proceed")
-        ret[rank] = (m.y0, m.get("cell"), int(m.scalar("population")))
+        _steps(m, steps, which.endswith("_graph"))
+        ret[rank] = (m.y0, m.get("cell"), int(m.scalar("population")), m.early_exchanges)
     else:
-        m = hydro_machine(size, device=dev, rank=rank, nranks=world)
+        m = hydro_machine(size, device=dev, rank=rank, nranks=world, fast=which.startswith("hydro_fast"))
         hydro_set_params(m, size)
         m.call("init")
-        for _ in range(steps):
-            m.call("proceed")
+        _steps(m, steps, which.endswith("_graph"))
         ret[rank] = (m.y0, {n: m.get(n) for n in ("density", "velocity0", "velocity1", "pressure")}, float(m.scalar("time")))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _steps(m, steps, graph):
+    """`steps` proceed() calls; with `graph`: two eager calls, then replays of a captured pair (Machine.capture)."""
+    if not graph:
+        for _ in range(steps):
+            m.call("proceed")
+        return
+    assert steps % 2 == 0 and steps >= 4
+    m.call("proceed"); m.call("proceed")
+    g = m.capture("proceed", 2)
+    for _ in range((steps - 2) // 2):
+        g.replay()
 
 
 def _multi(which, size, steps, port):
@@ -69,6 +80,41 @@ def test_life_two_gpus_equal_one_gpu():
     parts = _multi("life", size, steps, 29711)
     assert np.array_equal(m.get("cell"), np.concatenate([p[1] for p in parts], axis=0))
     assert all(p[2] == int(m.scalar("population")) for p in parts)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_life_two_gpus_boundary_first_and_graph_replay_equal_one_gpu():
+    """The stage is launched once per step in boundary-first chunk order, the ghost rows leave when the in-kernel signal
+    fires, and pairs of steps are replayed from a CUDA graph (NCCL send/recv captured): still bit-identical to one GPU."""
+    from paraiso_b200.machines import life_machine, life_seed
+    size, steps = (4096, 3000), 20
+    m = life_machine(size)
+    m.call("init")
+    m.set("cell", life_seed(size[0], 0, size[1]))
+    _steps(m, steps, True)       # the 1-GPU machine replays a graph too
+    parts = _multi("life_graph", size, steps, 29717)
+    assert all(p[3] >= 2 for p in parts), "the boundary-first path was not taken"
+    assert np.array_equal(m.get("cell"), np.concatenate([p[1] for p in parts], axis=0))
+    assert all(p[2] == int(m.scalar("population")) for p in parts)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("which", ["hydro_graph", "hydro_fast_graph"])
+def test_hydro_two_gpus_graph_replay_equal_one_gpu(which):
+    """Graph replay of step pairs on two GPUs (ghost rows + dt all-reduce inside the graph; the fast build also carries
+    its dt reduce from call to call) equals eager stepping on one GPU bit for bit."""
+    from paraiso_b200.machines import hydro_machine, hydro_set_params
+    size, steps = (1024, 777), 10
+    m = hydro_machine(size, fast=which.startswith("hydro_fast"))
+    hydro_set_params(m, size)
+    m.call("init")
+    for _ in range(steps):
+        m.call("proceed")
+    parts = _multi(which, size, steps, 29719 + (which == "hydro_graph"))
+    for n in ("density", "velocity0", "velocity1", "pressure"):
+        two = np.concatenate([p[1][n] for p in parts], axis=0)
+        assert np.array_equal(m.get(n).view(np.uint64), two.view(np.uint64)), n
+    assert all(p[2] == float(m.scalar("time")) for p in parts)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -154,3 +154,64 @@ def test_hydro_4096_three_steps():
         m.call("proceed"); o.call("proceed")
     for n in NAMES:
         assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
+
+
+@pytest.mark.parametrize("which", ["life", "hydro", "hydro_fast"])
+def test_graph_replay_equals_eager_stepping(which):
+    """Machine.capture: pairs of proceed() calls replayed from a CUDA graph give the state eager stepping gives, bit for bit;
+    a host write between replays invalidates the carried dt reduce baked into the fast build's graph (falls back to eager calls)."""
+    from paraiso_b200.machines import hydro_machine, hydro_set_params, life_machine, life_seed
+    def make():
+        if which == "life":
+            m = life_machine((1000, 777))
+            m.call("init")
+            m.set("cell", life_seed(1000, 0, 777))
+            return m, ["cell"], "population"
+        m = hydro_machine((700, 333), fast=which == "hydro_fast")
+        hydro_set_params(m, (700, 333))
+        m.call("init")
+        return m, NAMES, "time"
+    a, names, sc = make()
+    b, _, _ = make()
+    for _ in range(2):
+        a.call("proceed"); b.call("proceed")
+    g = a.capture("proceed", 2)
+    l0 = a.launches
+    for _ in range(4):
+        g.replay()
+        b.call("proceed"); b.call("proceed")
+    assert a.launches - l0 == 4 * g.launches_per_replay > 0
+    for n in names:
+        assert np.array_equal(a.get(n).view(np.uint8), b.get(n).view(np.uint8)), n
+    assert a.scalar(sc) == b.scalar(sc)
+    # a host write in between: replay must still equal eager stepping
+    for m in (a, b):
+        x = m.get(names[0]); x[5:9, 7:30] = x[10:14, 7:30]; m.set(names[0], x)
+    g.replay(); g.replay()
+    for _ in range(4):
+        b.call("proceed")
+    for n in names:
+        assert np.array_equal(a.get(n).view(np.uint8), b.get(n).view(np.uint8)), n
+    assert a.scalar(sc) == b.scalar(sc)
+
+
+def test_hydro_exact_build_with_denormal_velocities_is_bit_identical():
+    """Tiny and denormal transverse velocities (what the front of a spreading perturbation looks like after a few hundred
+    steps): the branch-free division hands those cells to the compiler's IEEE slow path, so the state still equals the
+    oracle's bit for bit — and the slow path really ran."""
+    size, steps = (256, 192), 6
+    m, o = _hydro_pair(size)
+    rng = np.random.default_rng(11)
+    for n in NAMES:
+        b = o.array(n)
+        if n == "velocity1":
+            mag = 10.0 ** rng.uniform(-323, -280, size=b.shape)
+            b[...] = np.where(rng.random(b.shape) < 0.3, mag * rng.choice([-1.0, 1.0], size=b.shape), 0.0)
+            b[::7, ::5] = 5e-324
+        m.set(n, b, with_margin=True)
+    for _ in range(steps):
+        m.call("proceed"); o.call("proceed")
+    for n in NAMES:
+        assert np.array_equal(m.get(n, with_margin=True).view(np.uint64), o.array(n).view(np.uint64)), n
+    assert m.scalar("time") == o.scalar("time")[0]
+    assert m.slow_path_cells() > 0

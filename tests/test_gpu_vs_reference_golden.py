@@ -104,3 +104,33 @@ def test_initialcondition_transcendentals_on_gpu():
     ok = np.isfinite(b)
     assert np.array_equal(np.isfinite(a), ok)
     assert np.max(np.abs(a[ok] - b[ok])) < 1e-12
+
+
+def test_hydro_master_float_on_gpu_against_the_reference_output_directly():
+    """The master program built in float for the B200, with its own init kernel, against cells sampled from the reference's
+    compiled Hydro.cpp (tests/golden/hydro_exampled_samples.npz): conserved variables within 1e-5 after 3 and 10 steps —
+    a pin of master's Hydro that does not pass through the oracle's front-end."""
+    import os
+    from paraiso_b200.build import build_machine
+    from paraiso_b200.examples.hydro import hydro_om, hydro_setup
+    from paraiso_b200.runtime import Machine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hydro_exampled_samples.npz"))
+    size = (1024, 1024)
+    desc, so = build_machine(hydro_setup(), hydro_om("master", real="Float"), tag="Hydro_OO_Float")
+    m = Machine(desc, so, size=size)
+    one = np.float32(1.0)
+    for k, v in dict(time=np.float32(0), cfl=np.float32(0.5), extent0=one, extent1=one, dR0=one / np.float32(1024), dR1=one / np.float32(1024)).items():
+        m.set_scalar(k, v)
+    m.call("init")
+
+    def cons(rho, u, v, p):
+        rho, u, v, p = (x.astype(np.float64) for x in (rho, u, v, p))
+        return [rho, rho * u, rho * v, p / (5.0 / 3.0 - 1.0) + 0.5 * rho * (u * u + v * v)]
+    for t in range(1, 11):
+        m.call("proceed")
+        if t in (3, 10):
+            got = cons(*[m.get(n)[::8, ::8] for n in NAMES])
+            want = cons(*[g[f"{n}_step{t}"] for n in NAMES])
+            for a, b in zip(got, want):
+                assert np.max(np.abs(a - b)) <= 1e-5 * np.max(np.abs(b)), t
+            assert abs(float(m.scalar("time")) - float(g[f"time_step{t}"][0])) <= 1e-5 * float(g[f"time_step{t}"][0])

@@ -118,6 +118,21 @@ def test_several_devices_print_what_one_device_prints(devices, life_exe, hydro_e
     assert hostclass.run(hydro_fast_exe, [4], devices=devices) == hostclass.run(hydro_fast_exe, [4])
 
 
+@pytest.mark.parametrize("devices", [2, 3])
+def test_tall_life_slabs_use_the_boundary_first_launch(devices, tmp_path):
+    """Slabs of several chunks: the class launches the stage once per device in boundary-first chunk order, waits for the
+    in-kernel signal (om_Life_wait_boundary) before the ghost-row send/recv, and prints what one device prints."""
+    import subprocess
+    from paraiso_b200.examples.life import life_om, life_setup
+    exe = str(tmp_path / "life_tall")
+    hostclass.link_emulated(life_setup("master", size=(64, 170)), life_om("master"), "Life_hostclass_tall", os.path.join(CPP, "life_driver.cpp"), exe)
+    one = hostclass.run(exe, [6])
+    env = dict(os.environ, OM_EMU_DEVICES=str(devices), OM_B200_GPUS=str(devices), OM_PRINT_EARLY="1")
+    r = subprocess.run([exe, "6"], check=True, capture_output=True, text=True, env=env, timeout=600)
+    assert r.stdout == one
+    assert int(r.stderr.split()[-1]) >= 6, r.stderr
+
+
 def test_class_rejects_more_devices_than_visible(life_exe):
     import subprocess
     r = subprocess.run([life_exe, "1"], capture_output=True, text=True, env=dict(os.environ, OM_EMU_DEVICES="2", OM_B200_GPUS="5"))

@@ -29,7 +29,7 @@ def _worker(rank, world, port, which, size, steps, ret):
         m.set("cell", life_seed(size[0], m.y0, m.nyl, nx_global=size[0]))
         for _ in range(steps):
             m.call("proceed")
-        ret[rank] = (m.y0, m.get("cell"), int(m.scalar("population")))
+        ret[rank] = (m.y0, m.get("cell"), int(m.scalar("population")), m.early_exchanges)
     else:
         from paraiso_b200.examples.hydro import hydro_om, hydro_setup
         from paraiso_b200.machines import hydro_set_params
@@ -89,6 +89,20 @@ def test_life_ranks_equal_one_rank(world):
     assert len(parts) == world
     assert np.array_equal(cell1, cell2)
     assert all(p[2] == pop1 for p in parts)      # all_reduce(sum) gives every rank the global population
+
+
+@pytest.mark.parametrize("world,size", [(2, (96, 120)), (3, (70, 170))])
+def test_life_boundary_first_launch_signals_and_equals_one_rank(world, size):
+    """Slabs tall enough for several chunks: the stage is launched once in boundary-first chunk order, the CTAs of the
+    first and the last chunk raise the "boundary rows written" flag (checked by the emulated om_wait_boundary), and the
+    result still equals the 1-rank run bit for bit (3 ranks: uneven slabs 57 + 57 + 56)."""
+    steps = 4
+    cell1, pop1 = _run("life", size, steps, 1, 0)
+    parts = _run("life", size, steps, world, 29631 + world)
+    assert all(p[3] >= steps for p in parts), "the boundary-first path was not taken"
+    cell2 = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=0)
+    assert np.array_equal(cell1, cell2)
+    assert all(p[2] == pop1 for p in parts)
 
 
 @pytest.mark.parametrize("world", [2, 3])      # 3 ranks: slabs of 13 + 12 + 12 rows, a middle rank without physical margins

@@ -105,3 +105,49 @@ def test_master_and_exampled_hydro_agree_in_double():
         a.call("proceed"); b.call("proceed")
     for n in NAMES:
         assert np.array_equal(a.array(n).view(np.uint64), b.array(n).view(np.uint64)), n
+
+
+def test_master_and_exampled_hydro_agree_in_double_256x256_20_steps():
+    """The longer version of the check above (every array bit for bit, 256x256, 20 steps): the program the BASELINE
+    configs run (master, double) is the pinned exampled program with other typing, not a second transcription that could
+    drift from it."""
+    size = (256, 256)
+    a = OracleMachine(hydro_setup(size), hydro_om("master"), openmp=True)
+    b = OracleMachine(hydro_setup(size), hydro_om("exampled", real="Double"), openmp=True)
+    for o in (a, b):
+        for k, v in dict(time=0.0, cfl=0.5, extent0=1.0, extent1=1.0, dR0=1.0 / size[0], dR1=1.0 / size[1]).items():
+            o.scalar(k)[0] = v
+        o.call("init")
+    for t in range(20):
+        a.call("proceed"); b.call("proceed")
+        if t in (0, 9, 19):
+            for n in NAMES:
+                assert np.array_equal(a.array(n).view(np.uint64), b.array(n).view(np.uint64)), (t, n)
+            assert a.scalar("time")[0] == b.scalar("time")[0]
+
+
+def _conserved32(rho, u, v, p):
+    rho, u, v, p = (x.astype(np.float64) for x in (rho, u, v, p))
+    return [rho, rho * u, rho * v, p / (5.0 / 3.0 - 1.0) + 0.5 * rho * (u * u + v * v)]
+
+
+def test_master_float_program_against_the_reference_output_directly():
+    """Decoupled pin for master's Hydro: the MASTER transcription (examples/hydro.py "master", Real = Float), run through the
+    oracle with its own init, against cells sampled from the reference's compiled Hydro.cpp (tests/golden/
+    hydro_exampled_samples.npz, every 8th interior cell after 3 and 10 steps) — conserved variables within the north
+    star's 1e-5.  A slip in the master program could not hide behind the front-end it shares with the oracle."""
+    g = np.load(os.path.join(GOLD, "hydro_exampled_samples.npz"))
+    size = (1024, 1024)
+    o = OracleMachine(hydro_setup(size), hydro_om("master", real="Float"), openmp=True)
+    one = np.float32(1.0)
+    for k, v in dict(time=np.float32(0), cfl=np.float32(0.5), extent0=one, extent1=one, dR0=one / np.float32(1024), dR1=one / np.float32(1024)).items():
+        o.scalar(k)[0] = v
+    o.call("init")
+    for t in range(1, 11):
+        o.call("proceed")
+        if t in (3, 10):
+            got = _conserved32(*[o.interior(n)[::8, ::8] for n in NAMES])
+            want = _conserved32(*[g[f"{n}_step{t}"] for n in NAMES])
+            for a, b in zip(got, want):
+                assert np.max(np.abs(a - b)) <= 1e-5 * np.max(np.abs(b)), t
+            assert abs(float(o.scalar("time")[0]) - float(g[f"time_step{t}"][0])) <= 1e-5 * float(g[f"time_step{t}"][0])
