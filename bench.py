@@ -201,7 +201,11 @@ def fp64_roofline(m, stage: int, kernel_ms: float, clocks):
         warp_rows = m.nx * m.nyl / 32.0 * e.overhead
         achieved = warp_rows * e.fp64 / (kernel_ms * 1e-3) / 1e9          # G warp-instructions / s
         peak = sms * 4 * 0.5 * sm_hz / 1e9
+        # issue roof: an FP64 warp instruction holds a scheduler's issue port for ~2 cycles, every other instruction for one
+        # (tools/ubench/fp64_issue.cu; the three builds of profiles/r2_hydro_exact_sweep.txt all sit at 0.93 of it)
+        issue = warp_rows * (e.instructions + e.fp64) / (kernel_ms * 1e-3) / 1e9 / (sms * 4 * sm_hz / 1e9)
         return {"bound": "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s", "frac": achieved / peak,
+                "issue_roof_frac": issue, "issue_roof_model": "(instructions + FP64 instructions) issue cycles per warp-row per scheduler",
                 "fp64_instr_per_warp_row": e.fp64, "instr_per_warp_row": e.instructions, "overhead": e.overhead,
                 "registers": e.registers, "ctas_per_sm": e.ctas_per_sm,
                 "source": "static SASS count of the row loop (cuobjdump) x measured kernel time; peak = one FP64 warp instruction per two cycles per scheduler"}
@@ -337,6 +341,23 @@ def main():
         for _ in range(3):
             m.call_stage("proceed", dom)
         return timed([lambda: m.call_stage("proceed", dom)] * args.steps) / args.steps
+
+    def per_rank(m, dom):
+        """[{rank, kernel_ms, slow_path_cells}] — this rank's own device time of the dominant stage (no max over ranks)."""
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            m.call_stage("proceed", dom)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        mine = torch.tensor([e0.elapsed_time(e1) / 5.0, float(m.slow_path_cells())], device=dev, dtype=torch.float64)
+        rows = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(rows, mine)
+        else:
+            rows = [mine]
+        return [dict(rank=i, kernel_ms=float(r[0].item()), slow_path_cells=int(r[1].item())) for i, r in enumerate(rows)]
 
     def e2e_block(m, arrays, cells_global):
         """(per-step pipeline, steady state) through the host API with pinned HOST buffers, copies inside the timed region."""
@@ -494,7 +515,7 @@ def main():
                             "frac": achieved / peak, "traffic": measured_traffic(m, kinfo["stages"][dom]["symbol"], "_" + build), "peak_source": peak_src,
                             "algorithmic_bytes_per_cell": ALG_BYTES["hydro"], "kernel_ms": kms,
                             "fp64_pipe": fp64_roofline(m, dom, kms, r["clocks"]) if rank == 0 else None},
-               "gpu_launches": r["launches"], "clocks": r["clocks"]}
+               "gpu_launches": r["launches"], "clocks": r["clocks"], "per_rank": per_rank(m, dom)}
         checks = {}
         if not args.no_verify:
             fin, same_t = hydro_state_ok(m)

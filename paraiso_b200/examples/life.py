@@ -73,7 +73,8 @@ def life_setup(variant: str = "master", size=None) -> Setup:
         s = Setup(local_size=size or (80, 48), boundary=(CYCLIC, CYCLIC), directory="./dist/")
     else:
         s = Setup(local_size=size or (128, 128), boundary=(OPEN, OPEN), directory="./dist/")  # LifeMain.hs:121-125
-    # winners of the sweeps in profiles/r1_life_sweep.txt: three rows in flight per CTA, 24-row chunks
+    # winners of the sweeps in profiles/r1_life_sweep.txt: three rows in flight per CTA; chunk height re-swept in round 2 with
+    # balanced chunks (profiles/r2o_life_chunks.jsonl: 832 chunks of 19.7 rows = 20 waves of CTAs, 0.3548 ms; 656 of 25: 0.3602)
     s.tuning.prefetch_rows = 3
-    s.tuning.chunk_rows_light = 24
+    s.tuning.chunk_rows_light = 20
     return s

@@ -700,7 +700,14 @@ class StageEmitter:
             ident = {"Sum": f"({T})0", "Min": self.type_max(v), "Max": self.type_min(v)}[rop]
             E(f"  {T} acc{slot} = {ident};   // reduce slot {slot}")
         if self.uses_range_flag:
-            E("  unsigned om_bad = 0u;   // sticky: this thread stored a NaN / Inf / denormal (om_div_rn / om_sqrt_rn are IEEE-correct for normal operands)")
+            E("  unsigned om_bad = 0u;   // sticky: this thread stored a NaN / Inf (om_div_rn / om_sqrt_rn, om_runtime.cuh)")
+            if self.depth:
+                # While a chunk's pipeline fills, scopes read ring rows nobody has written yet.  Nothing computed from them reaches a
+                # stored cell, but whatever the previous kernel left in shared memory is then an operand: after an NCCL kernel that is
+                # integer data, i.e. denormals as doubles, and every such lane sent its cell to the IEEE slow path (10 000 cells per
+                # launch on two GPUs, 2x the kernel time).  Zeros are benign operands.
+                E(f"  for (int i = tid; i < {self.smem_bytes() // 16}; i += NT) reinterpret_cast<int4*>(om_smem)[i] = make_int4(0, 0, 0, 0);")
+                E("  __syncthreads();")
         for (d, c), nm in sorted(self.slotvars.items()):
             E(f"  int {nm} = ((((jbeg + {c}) % {d}) + {d}) % {d}) * RW;")
         if self.window:

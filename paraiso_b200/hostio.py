@@ -40,20 +40,34 @@ def pin_to_gpu_numa(index: int) -> dict:
     """Restrict this process to the CPUs of the GPU's NUMA node (so that pinned host buffers allocated afterwards are
     first-touched there and the copy engines do not cross the socket interconnect).  Returns what was done."""
     node = gpu_numa_node(index)
-    info = {"numa_node": node, "cpus": None}
-    if node is None:
-        return info
+    info = {"numa_node": node, "cpus": None, "source": None}
+    cpus = None
     try:
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set(_cpulist(f.read()))
+        if node is not None:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus, info["source"] = set(_cpulist(f.read())), "sysfs"
+        else:
+            cpus, info["source"] = nvml_cpu_affinity(index), "nvml"
         allowed = set(os.sched_getaffinity(0))
-        use = sorted(cpus & allowed)
-        if use:
+        use = sorted((cpus or set()) & allowed)
+        if use and len(use) < len(allowed):
             os.sched_setaffinity(0, use)
             info["cpus"] = len(use)
     except Exception as e:      # placement is an optimisation only
         info["error"] = repr(e)[:120]
     return info
+
+
+def nvml_cpu_affinity(index: int):
+    """CPUs NVML calls ideal for the GPU (the cores of its NUMA node), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        return {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+    except Exception:
+        return None
 
 
 class HostPipeline:

@@ -130,6 +130,7 @@ class Machine:
         self.statics = desc["statics"]
         self.index = {s["name"]: i for i, s in enumerate(self.statics)}
         self._storage: List[torch.Tensor] = []
+
         self.cur: List[Optional[torch.Tensor]] = []
         self.alt: List[Optional[torch.Tensor]] = []
         for s in self.statics:
@@ -141,6 +142,7 @@ class Machine:
                     full = torch.zeros((self.planes * self.rows + 2 * APRON, self.pitch), dtype=t, device=self.device)
                     self._storage.append(full)
                     lst.append(full[APRON:APRON + self.planes * self.rows])
+
             else:
                 self.cur.append(None)
                 self.alt.append(None)
@@ -168,6 +170,7 @@ class Machine:
                 self._fn[k["scalars"]] = f
         self.launches = 0
         self.wave_round = True       # light stages: round the chunk count to whole waves of resident CTAs (see _geom)
+        self.force_chunks = 0        # tuning tools: this many chunks per strip for light stages (0: the rule of _geom)
         self.early_exchanges = 0     # stage launches whose ghost-row exchange was triggered by the in-kernel boundary signal
         self._geom_cache: Dict[str, OmGeom] = {}
         self._partial: Dict[int, dict] = {}     # static scalar index -> pending all_reduce description
@@ -233,6 +236,8 @@ class Machine:
             whole = (k * wave) // (strips * layers)
             if self.wave_round and whole >= 1 and abs(whole - chunks) <= 0.08 * chunks:
                 chunks = whole
+            if self.force_chunks:
+                chunks = self.force_chunks
         # the reduction scratch holds one partial per CTA: very large slabs get fewer, taller chunks instead of more CTAs
         if strips * chunks * layers > self.max_blocks and strips * layers <= self.max_blocks:
             chunks = self.max_blocks // (strips * layers)

@@ -1,0 +1,24 @@
+"""Life 16384^2: kernel time against the number of row chunks per strip (launch geometry only — one build).  The default rule
+(runtime.Machine._geom) rounds rows / Tuning.chunk_rows_light to whole waves of resident CTAs."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from paraiso_b200.machines import life_machine, life_seed  # noqa: E402
+from paraiso_b200.tuning import measure  # noqa: E402
+
+size = (16384, 16384)
+m = life_machine(size)
+m.call("init")
+m.set_from_host("cell", torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory())
+st = m.kernels["proceed"]["stages"][0]
+occ = getattr(m.lib, st["symbol"] + "_occupancy")()
+for chunks in [0, 541, 582, 624, 640, 655, 656, 660, 666, 675, 683, 707, 749, 790, 832, 1000, 1332]:
+    m.force_chunks = chunks
+    m._geom_cache.clear()
+    ms = min(measure(m, "proceed", steps=20, stage=0) for _ in range(3))
+    g = m._geom(st)
+    print(json.dumps(dict(chunks=g.nchunks, forced=chunks, rows_per_chunk=16384 / g.nchunks, ctas=g.nchunks * 32, waves=g.nchunks * 32 / (148 * occ),
+                          ms=ms, GBs=2 * 4 * 16384 * 16384 / ms / 1e6)), flush=True)
