@@ -178,6 +178,7 @@ class Machine:
         self._carry_kernel: Optional[str] = None   # kernel whose carried reduces are valid for its next call
         self._comm_event = None
         self._comm_stream = torch.cuda.Stream(self.device, priority=-1) if (self.device.type == "cuda" and nranks > 1) else None
+        self._ar_group = group
         if self._comm_stream is not None and group is None:
             import torch.distributed as dist
             if dist.is_initialized() and dist.get_backend() == "nccl" and dist.get_world_size() == nranks:
@@ -223,8 +224,17 @@ class Machine:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 4
         layers = self.own_z1 - self.own_z0
         if st.get("chunk_rows", 0) <= 0:
-            # heavy (shared-memory) stages: one full wave of equally long CTAs
-            chunks = max(1, min((sms * occ) // strips, nrows // max(32, 8 * (st["warmup"] + 2))))
+            # heavy (shared-memory) stages: few, long chunks — every chunk pays the pipeline fill (warm-up rows) again — whose
+            # CTAs fill whole waves of resident CTAs: the count that maximises (fill of the last wave) x (useful rows per
+            # chunk).  Hydro 4096^2: 34 strips x 13 chunks = 442 of 444 slots, one wave; a 32768-wide slab has 269 strips,
+            # where "one wave" meant ONE chunk and 269 CTAs on 444 slots (round 1) — now 13 chunks, 3497 CTAs in 8 waves.
+            wave, fill = sms * occ, st["warmup"] + 2
+            best, chunks = -1.0, 1
+            for c in range(1, max(1, nrows // max(32, 8 * fill)) + 1):
+                ctas = strips * c * layers
+                score = ctas / (-(-ctas // wave) * wave) * (nrows / c) / (nrows / c + fill)
+                if score > best + 1e-9:
+                    best, chunks = score, c
         else:
             # light streaming stages: short chunks (Tuning.chunk_rows_light, measured in profiles/r1_life_sweep.txt)
             # keep the set of concurrently streamed rows compact; warm-up rows are L2 hits.  The count is then rounded to
@@ -400,7 +410,9 @@ class Machine:
         import torch.distributed as dist
         op = {"Sum": dist.ReduceOp.SUM, "Min": dist.ReduceOp.MIN, "Max": dist.ReduceOp.MAX}[r["op"]]
         view = self.sc[r["slot"]:r["slot"] + 1].view(TORCH_TYPE[r["type"]])[:1]
-        dist.all_reduce(view, op=op, group=self.group)   # 4-byte types reduce the low half of the slot; the rest stays zero
+        # (the default group when the ghost rows travel on the high-priority one: two communicators, so that the exchange on the
+        #  communication stream and this all-reduce on the compute stream run side by side instead of queueing behind each other)
+        dist.all_reduce(view, op=op, group=self._ar_group)   # 4-byte types reduce the low half of the slot; the rest stays zero
 
     def _exchange_rows(self, arrays):
         """Ghost rows <- neighbours' boundary interior rows (full pitch, so x ghosts travel too), for one array or a list
