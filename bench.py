@@ -39,6 +39,8 @@ HYDRO_SIZE = (4096, 4096)       # per GPU
 HYDRO32K = (32768, 32768)       # global
 ALG_BYTES = {"life": 8, "hydro": 64}                 # algorithmic bytes per cell update
 CPU_SAMPLE = {"life": (16384, 16384), "hydro": (1024, 1024)}
+if os.environ.get("OM_BENCH_TEST_SAMPLE"):      # tests/test_bench_contract.py only: a small grid for the checks that are not about the size
+    CPU_SAMPLE = {"life": (2048, 2048), "hydro": (256, 256)}
 HYDRO_ARRAYS = ["density", "velocity0", "velocity1", "pressure"]
 
 

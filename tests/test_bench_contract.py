@@ -35,7 +35,7 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_forces_the_openmp_thread_count():
     """torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm must still use every core it may run on and
     report the count OpenMP really uses."""
-    r = _bench("--impl", "reference", "--steps", "1", "--warmup", "0", env={"OMP_NUM_THREADS": "1"})
+    r = _bench("--impl", "reference", "--steps", "1", "--warmup", "0", env={"OMP_NUM_THREADS": "1", "OM_BENCH_TEST_SAMPLE": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.strip().split("\n") if l.startswith("{")][0])
     want = len(os.sched_getaffinity(0))
