@@ -165,6 +165,13 @@ class StageEmitter:
             self.wcmin = min(i.lag - i.depth + 1 for i in self.ring_inputs)
             self.wcmax = max(i.lag for i in self.ring_inputs)
             self.U = self.wcmax - self.wcmin + 1
+        # grouped staging (Tuning.barrier_group): the rows of one window rotation are staged together behind one CTA barrier;
+        # the bodies of a group only read the row that enters the window, so 2 U ring rows suffice (readers of group g use rows
+        # [j + lag, j + lag + U), the staging of group g + 1 behind the same barrier writes [j + lag + U, j + lag + 2 U))
+        self.grouped = self.window and not self.bulk and bool(getattr(self.tuning, "barrier_group", False))
+        if self.grouped:
+            for i in self.ring_inputs:
+                self.depth[i.vid] = 2 * self.U
         # inputs read without staging (column offset 0 only) are prefetched one row ahead into registers
         self.direct_pf = bool(self.tuning.direct_prefetch) and not self.window
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
@@ -536,7 +543,8 @@ class StageEmitter:
         mlx, mhx = self.margin_lo[0], self.margin_hi[0]
         warm = st.warmup
         has_ring_in = bool(self.ring_inputs)
-        lead = warm + (self.PF if has_ring_in else 0)
+        lead = warm + (self.PF if (has_ring_in and not self.grouped) else 0)
+        self.post_init: List[str] = []      # statements between the declarations and the row loop (grouped staging: the first group)
 
         # ---- loop body first (it registers slot counters, hoisted values, uniform nodes) -------
         def stage_inputs(B, row_shift: int):
@@ -585,18 +593,49 @@ class StageEmitter:
 
         nph = max(len(st.phases), st.out_level)
         bodies: List[List[str]] = []
+        def stage_row(out, c: int, guard: str, ind: str):
+            """cp.async of one row of every ring input into the slot of row (group base + c)."""
+            out.append(f"{ind}if ({guard}) {{")
+            for i in self.ring_inputs:
+                v, T = i.vid, self.T(i.vid)
+                nb = TYPE_BYTES[i.ctype] * V
+                so = self.slot_off(self.depth[v], i.lag + c)
+                ln = f"const {T}* __restrict__ src{v} = {self.inp(v)} + (ptrdiff_t)(jbeg + {i.lag}) * g.pitch + tc;   // advances one row per staged row"
+                if ln not in self.pre:
+                    self.pre.append(ln)
+                out.append(f"{ind}  om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
+                if self.PL:
+                    out.append(f"{ind}  if (tid < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + tid * V], src{v} - PL, {nb});")
+                if self.PR:
+                    out.append(f"{ind}  if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
+                out.append(f"{ind}  src{v} += g.pitch;")
+            out.append(f"{ind}}}")
+
+        group_top: List[str] = []
+        if self.window and self.grouped:
+            # the first group is staged before the loop; every group then waits for its own rows, synchronises the CTA once and
+            # stages the next group (rows beyond the chunk's last needed row are not fetched)
+            for u in range(self.U):
+                stage_row(self.post_init, u, f"jbeg + {u} < r1", "")
+            self.post_init.append("om_cp_async_commit();")
+            group_top.append("om_cp_async_wait<0>();")
+            group_top.append("__syncthreads();")
+            for u in range(self.U):
+                stage_row(group_top, self.U + u, f"j + {self.U + u} < r1", "")
+            group_top.append("om_cp_async_commit();")
         if self.window:
             # one unrolled body per window row: the register sets rotate by renaming
             wregs: Dict[str, str] = {}
             for u in range(self.U):
                 self.window_u = u
                 B: List[str] = []
-                stage_inputs(B, 0)
-                B.append("__syncthreads();")
+                if not self.grouped:
+                    stage_inputs(B, 0)
+                    B.append("__syncthreads();")
                 B.append("// the row that enters the stencil window: shared memory -> registers, once")
                 for i in self.ring_inputs:
                     b, T = i.vid, self.T(i.vid)
-                    so = self.slot_off(self.depth[b], i.lag)
+                    so = self.slot_off(self.depth[b], i.lag + (u if self.grouped else 0))
                     sset = (u + i.lag - self.wcmin) % self.U
                     vt = VEC_TYPE.get((T, V))
                     names = [f"w{b}_{sset}_{_m(o)}" for o in range(-i.rd_xlo, V + i.rd_xhi)]
@@ -615,35 +654,50 @@ class StageEmitter:
             self.window_u = None
             self.wregs = wregs
         else:
-            B = []
-            if has_ring_in:
-                stage_inputs(B, 0)
-            B.append("__syncthreads();")
-            for lvl in range(1, nph + 1):
-                if lvl > 1:
-                    B.append("__syncthreads();")
-                mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
-                lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
-                for a in lags:
-                    grp = [m for m in mats_here if st.mats[m].lag == a]
-                    early = min(st.mats[m].early for m in grp)
-                    B.append(f"if (j >= r0 - {-early}) {{   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
-                    B.append(f"  const int row = j + {a};")
-                    lines, res = self.scope_guarded(grp, a)
-                    B += ["  " + l for l in lines]
-                    for m in grp:
-                        so = self.slot_off(self.depth[m], a)
-                        T = self.T(m)
-                        vt = VEC_TYPE.get((T, V))
-                        if vt:
-                            B.append(f"  *reinterpret_cast<{vt}*>(&ring{m}[{so} + tb]) = make_{vt}({', '.join(res[(m, k)] for k in range(V))});")
-                        else:
-                            for k in range(V):
-                                B.append(f"  ring{m}[{so} + tb + {k}] = {res[(m, k)]};")
-                    B.append("}")
-                if lvl == st.out_level:
-                    B += self.emit_out()
-            bodies.append(self.loop_top + B)
+            def build(mode: str) -> List[str]:
+                """One row iteration.  "steady" (j >= r0, all but the first rows of a chunk): every scope runs and the row is
+                stored — no tests, so the code between two barriers is one basic block the compiler can schedule across the
+                scopes; "fill": the first rows of a chunk, each scope behind its own start test, nothing stored yet;
+                "both": one body for all rows (every scope and the stores behind their tests)."""
+                steady = mode == "steady"
+                B: List[str] = []
+                if has_ring_in:
+                    stage_inputs(B, 0)
+                B.append("__syncthreads();")
+                for lvl in range(1, nph + 1):
+                    if lvl > 1:
+                        B.append("__syncthreads();")
+                    mats_here = st.phases[lvl - 1] if lvl - 1 < len(st.phases) else []
+                    lags = sorted({st.mats[m].lag for m in mats_here}, key=lambda a: min(m for m in mats_here if st.mats[m].lag == a))
+                    for a in lags:
+                        grp = [m for m in mats_here if st.mats[m].lag == a]
+                        early = min(st.mats[m].early for m in grp)
+                        head = "{" if steady else f"if (j >= r0 - {-early}) {{"
+                        B.append(f"{head}   // phase {lvl}: row j+{a} of {len(grp)} intermediate(s)")
+                        B.append(f"  const int row = j + {a};")
+                        lines, res = self.scope_guarded(grp, a)
+                        B += ["  " + l for l in lines]
+                        for m in grp:
+                            so = self.slot_off(self.depth[m], a)
+                            T = self.T(m)
+                            vt = VEC_TYPE.get((T, V))
+                            if vt:
+                                B.append(f"  *reinterpret_cast<{vt}*>(&ring{m}[{so} + tb]) = make_{vt}({', '.join(res[(m, k)] for k in range(V))});")
+                            else:
+                                for k in range(V):
+                                    B.append(f"  ring{m}[{so} + tb + {k}] = {res[(m, k)]};")
+                        B.append("}")
+                    if lvl == st.out_level and mode != "fill":
+                        B += self.emit_out(guard="true" if steady else "j >= r0")
+                return B
+            fill_body = None
+            if st.mats and self.tuning.peel_fill:
+                # two row loops: the first rows of a chunk (pipeline fill), then the steady rows — instead of a start test per scope
+                steady = build("steady")
+                fill_body = self.loop_top + build("fill")
+                bodies.append(self.loop_top + steady)
+            else:
+                bodies.append(self.loop_top + build("both"))
 
         # ---- assemble -----------------------------------------------------------------------------
         L: List[str] = []
@@ -716,20 +770,37 @@ class StageEmitter:
                 byT.setdefault(T, []).append(n_)
             for T, ns in byT.items():
                 E(f"  {T} " + ", ".join(f"{n_} = 0" for n_ in sorted(ns)) + ";   // stencil window (rotates by renaming)")
+        for l in self.post_init:
+            E("  " + l)
         nb_ = len(bodies)
-        E(f"  for (int j = jbeg; j < r1; j += {nb_}) {{")
+        if not self.window and fill_body is not None:
+            E("  int j = jbeg;")
+            E("  for (; j < min(r0, r1); ++j) {   // pipeline fill: every scope behind its own start test, nothing stored")
+            L += ["    " + l for l in fill_body]
+            for (d, c), nm in sorted(self.slotvars.items()):
+                E(f"    {nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+            E("  }")
+            E("  for (; j < r1; ++j) {   // steady rows: one basic block between barriers")
+        else:
+            E(f"  for (int j = jbeg; j < r1; j += {nb_}) {{")
+        L += ["    " + l for l in group_top]
         for u, B in enumerate(bodies):
             if nb_ > 1:
                 E(f"    if (j + {u} < r1) {{")
             L += [("      " if nb_ > 1 else "    ") + l for l in B]
-            # slot offsets are relative to the body's own row, so they advance after every body
+            # slot offsets are relative to the body's own row, so they advance after every body (grouped staging: relative to the
+            # group's first row; they advance by U rows after the group)
             for (d, c), nm in sorted(self.slotvars.items()):
-                E(("      " if nb_ > 1 else "    ") + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+                if not self.grouped:
+                    E(("      " if nb_ > 1 else "    ") + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
             if self.bulk:
                 ind = "      " if nb_ > 1 else "    "
                 E(ind + f"++it; if (++bar_i == {self.NBAR}) bar_i = 0; if (++bar_w == {self.NBAR}) {{ bar_w = 0; bar_wp ^= 1; }}")
             if nb_ > 1:
                 E("    }")
+        if self.grouped:
+            for (d, c), nm in sorted(self.slotvars.items()):
+                E(f"    {nm} += {self.U} * RW; if ({nm} >= {d} * RW) {nm} -= {d} * RW;")
         E("  }")
         if self.uses_range_flag:
             E("  if (om_bad) red_counter[OM_SIG_RANGE] = 1u;   // the host raises at its next synchronisation point")
@@ -793,9 +864,13 @@ class StageEmitter:
         P("const int out_lo = max(cx0, strip_lo), out_hi = min(cx1, strip_lo + W_OUT);   // this CTA's output columns")
         P("const bool li_all = (tc >= out_lo) && (tc + V <= out_hi);                     // whole vector inside")
         P("const bool li_any = (tc + V > out_lo) && (tc < out_hi);")
-        P("const bool edge_x = g.cyc_x && (strip_lo < g.xorg + g.gx_hi || strip_lo + W_OUT > g.xorg + g.nx - g.gx_lo);")
-        P("const bool edge_y = g.wrap_y_local && (r0 < g.yorg + g.gy_hi || r1 > g.yorg + g.nyl - g.gy_lo);")
-        P("const bool edge_any = edge_x || edge_y;   // this CTA writes cells that have a ghost copy")
+        # ghost-cell writes exist only in machines generated with a Cyclic axis (the boundary kinds are baked into the kernels:
+        # margins, Valid masks); Open / Open machines (Hydro) carry neither the predicates nor the branch per store
+        cyclic = any(b == CYCLIC for b in self.plan.setup.boundary)
+        if cyclic:
+            P("const bool edge_x = g.cyc_x && (strip_lo < g.xorg + g.gx_hi || strip_lo + W_OUT > g.xorg + g.nx - g.gx_lo);")
+            P("const bool edge_y = g.wrap_y_local && (r0 < g.yorg + g.gy_hi || r1 > g.yorg + g.nyl - g.gy_lo);")
+            P("const bool edge_any = edge_x || edge_y;   // this CTA writes cells that have a ghost copy")
         B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
         B.append(f"  const int row = {row_expr};")
         lines, res = self.scope_guarded(targets, 0)
@@ -828,7 +903,8 @@ class StageEmitter:
             for (s_, v_) in st.store_targets:
                 if self.ops[v_].ctype == "Double":
                     B.append("  if (li_any) om_bad |= " + " | ".join(
-                        f"((tc + {k} >= out_lo && tc + {k} < out_hi) ? om_state_bad({oname(v_, splane(s_, v_), k)}) : 0u)" for k in range(V)) + ";")
+                        (f"om_state_bad({oname(v_, splane(s_, v_), k)})" if V == 1 else
+                         f"((tc + {k} >= out_lo && tc + {k} < out_hi) ? om_state_bad({oname(v_, splane(s_, v_), k)}) : 0u)") for k in range(V)) + ";")
         if need_gmy:
             idx = B.index(f"  const int row = {row_expr};")
             B.insert(idx + 1, f"  const int gmy = row - g.yorg + g.y0 + {mly}; const int memy = g.ny + {mly + mhy};   // row in the reference memory box")
@@ -853,29 +929,35 @@ class StageEmitter:
                 for k in range(V):
                     B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
                 B.append("    }")
+            elif V == 1:
+                B.append(f"    if (li_any) p[0] = {on[0]};")
             else:
                 for k in range(V):
                     B.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
             # fused ghost-cell writes for Cyclic axes: the wrap the reference evaluates with % on every
             # read (PlanTrans.hs:477-484) is materialised once per written cell
-            B.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
-            for k in range(V):
-                B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
-                B.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
-                B.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
-                B.append(f"        if (dc) p[{k} + dc] = {on[k]};")
-                B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = {on[k]};")
-                B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = {on[k]};")
-                B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]};   // domain narrower than the ghost width")
-                B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = {on[k]};")
-                B.append("      }")
-            B.append("    } }")
+            if cyclic:
+                B.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
+                for k in range(V):
+                    B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
+                    B.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
+                    B.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
+                    B.append(f"        if (dc) p[{k} + dc] = {on[k]};")
+                    B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                    B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                    B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]};   // domain narrower than the ghost width")
+                    B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = {on[k]};")
+                    B.append("      }")
+                B.append("    } }")
             B.append("  }" + ("}" if zo else ""))
         def accumulate(v, rop, slot, names, ind):
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             chain = f"acc{slot}"
             for k in range(V):
                 chain = f"{cls}::op({chain}, {names[k]})"
+            if V == 1:
+                B.append(f"{ind}if (li_any) {{ acc{slot} = {chain}; }}")
+                return
             B.append(f"{ind}if (li_all) {{ acc{slot} = {chain}; }}")
             B.append(f"{ind}else if (li_any) {{")
             for k in range(V):

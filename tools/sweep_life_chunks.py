@@ -9,16 +9,39 @@ import torch  # noqa: E402
 from paraiso_b200.machines import life_machine, life_seed  # noqa: E402
 from paraiso_b200.tuning import measure  # noqa: E402
 
+from paraiso_b200.build import build_machine  # noqa: E402
+from paraiso_b200.examples.life import life_om, life_setup  # noqa: E402
+from paraiso_b200.runtime import Machine  # noqa: E402
+
 size = (16384, 16384)
-m = life_machine(size)
-m.call("init")
-m.set_from_host("cell", torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory())
-st = m.kernels["proceed"]["stages"][0]
-occ = getattr(m.lib, st["symbol"] + "_occupancy")()
-for chunks in [0, 541, 582, 624, 640, 655, 656, 660, 666, 675, 683, 707, 749, 790, 832, 1000, 1332]:
-    m.force_chunks = chunks
-    m._geom_cache.clear()
-    ms = min(measure(m, "proceed", steps=20, stage=0) for _ in range(3))
-    g = m._geom(st)
-    print(json.dumps(dict(chunks=g.nchunks, forced=chunks, rows_per_chunk=16384 / g.nchunks, ctas=g.nchunks * 32, waves=g.nchunks * 32 / (148 * occ),
-                          ms=ms, GBs=2 * 4 * 16384 * 16384 / ms / 1e6)), flush=True)
+seed = torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory()
+
+
+def variants():
+    """(label, machine): the default build and the one with a CTA barrier per row (Tuning.barrier_group = False)."""
+    yield "barrier per group", life_machine(size)
+    s = life_setup("master")
+    s.tuning.barrier_group = False
+    desc, so = build_machine(s, life_om("master"), tag="Life_CC_rowbarrier")
+    yield "barrier per row", Machine(desc, so, size=size)
+
+
+if __name__ == "__main__":
+    if "--prebuild" in sys.argv:
+        s = life_setup("master")
+        s.tuning.barrier_group = False
+        build_machine(s, life_om("master"), tag="Life_CC_rowbarrier")
+        sys.exit(0)
+    for label, m in variants():
+        m.call("init")
+        m.set_from_host("cell", seed)
+        st = m.kernels["proceed"]["stages"][0]
+        occ = getattr(m.lib, st["symbol"] + "_occupancy")()
+        for chunks in [0, 444, 512, 541, 582, 624, 656, 666, 707, 749, 790, 832, 874, 915, 1000, 1332]:
+            m.force_chunks = chunks
+            m._geom_cache.clear()
+            ms = min(measure(m, "proceed", steps=20, stage=0) for _ in range(3))
+            g = m._geom(st)
+            print(json.dumps(dict(variant=label, occupancy=occ, chunks=g.nchunks, forced=chunks, rows_per_chunk=16384 / g.nchunks, ctas=g.nchunks * 32,
+                                  waves=g.nchunks * 32 / (148 * occ), ms=ms, GBs=2 * 4 * 16384 * 16384 / ms / 1e6)), flush=True)
+        del m
