@@ -77,4 +77,5 @@ def life_setup(variant: str = "master", size=None) -> Setup:
     # balanced chunks (profiles/r2o_life_chunks.jsonl: 832 chunks of 19.7 rows = 20 waves of CTAs, 0.3548 ms; 656 of 25: 0.3602)
     s.tuning.prefetch_rows = 3
     s.tuning.chunk_rows_light = 20
+    s.tuning.min_blocks = 9          # 9 CTAs of 128 threads per SM: at most 56 registers (the steady-state copy of the row loop asks for 60)
     return s

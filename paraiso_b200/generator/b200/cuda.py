@@ -121,6 +121,7 @@ class StageEmitter:
         self.tuning = plan.setup.tuning
         self.newton = (not self.fast) and self.tuning.exact_divsqrt == "newton"   # branch-free IEEE-correct Double division / sqrt
         self.uses_range_flag = False
+        self._steady = False          # emitting the steady-state copy of a row-window body (no start / end tests)
         self._ieee_scope = False      # emitting the cold clone of a scope: the compiler's own IEEE division / sqrt
         self._guarded_ops = 0         # guarded divisions / square roots emitted by the scope() call in progress
         self.PF = self.tuning.prefetch_rows     # cp.async prefetch distance in rows
@@ -572,7 +573,7 @@ class StageEmitter:
             # (short chunks only, i.e. row-window stages: in the heavy stages' one-wave chunks of hundreds of rows the test
             #  saves nothing and costs the flux kernel 4 %)
             jx = "j" if self.window_u is None else f"j + {self.window_u}"
-            B.append(f"if ({jx} + {self.PF} < r1) {{" if self.window else "{")
+            B.append(f"if ({jx} + {self.PF} < r1) {{" if (self.window and not self._steady) else "{")
             for i in self.ring_inputs:
                 v = i.vid
                 T = self.T(v)
@@ -623,10 +624,14 @@ class StageEmitter:
             for u in range(self.U):
                 stage_row(group_top, self.U + u, f"j + {self.U + u} < r1", "")
             group_top.append("om_cp_async_commit();")
+        steady_bodies: List[List[str]] = []
         if self.window:
             # one unrolled body per window row: the register sets rotate by renaming
             wregs: Dict[str, str] = {}
-            for u in range(self.U):
+            for u in list(range(self.U)) * (2 if (self.tuning.peel_fill and not self.grouped) else 1):
+                # (second pass: the steady-state copies — every row of the group is stored and every staged row is needed, so the
+                #  per-row tests go and a group is tested once, CTA-uniformly)
+                self._steady = len(bodies) == self.U
                 self.window_u = u
                 B: List[str] = []
                 if not self.grouped:
@@ -649,8 +654,9 @@ class StageEmitter:
                             B.append(f"w{b}_{sset}_{kk} = ring{b}[{so} + tb + {kk}];")
                     for o in list(range(-i.rd_xlo, 0)) + list(range(V, V + i.rd_xhi)):
                         B.append(f"w{b}_{sset}_{_m(o)} = ring{b}[{so} + tb + ({o})];")
-                B += self.emit_out(row_expr=f"j + {u}", guard=f"j + {u} >= r0")
-                bodies.append(B)
+                B += self.emit_out(row_expr=f"j + {u}", guard="true" if self._steady else f"j + {u} >= r0")
+                (steady_bodies if self._steady else bodies).append(B)
+            self._steady = False
             self.window_u = None
             self.wregs = wregs
         else:
@@ -784,20 +790,31 @@ class StageEmitter:
         else:
             E(f"  for (int j = jbeg; j < r1; j += {nb_}) {{")
         L += ["    " + l for l in group_top]
-        for u, B in enumerate(bodies):
-            if nb_ > 1:
-                E(f"    if (j + {u} < r1) {{")
-            L += [("      " if nb_ > 1 else "    ") + l for l in B]
-            # slot offsets are relative to the body's own row, so they advance after every body (grouped staging: relative to the
-            # group's first row; they advance by U rows after the group)
-            for (d, c), nm in sorted(self.slotvars.items()):
-                if not self.grouped:
-                    E(("      " if nb_ > 1 else "    ") + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
-            if self.bulk:
-                ind = "      " if nb_ > 1 else "    "
-                E(ind + f"++it; if (++bar_i == {self.NBAR}) bar_i = 0; if (++bar_w == {self.NBAR}) {{ bar_w = 0; bar_wp ^= 1; }}")
-            if nb_ > 1:
-                E("    }")
+
+        def emit_bodies(bs, tested: bool, ind0: str):
+            for u, B in enumerate(bs):
+                wrap = nb_ > 1 and tested
+                if wrap:
+                    E(f"{ind0}if (j + {u} < r1) {{")
+                ind = ind0 + ("  " if wrap else "")
+                L.extend(ind + l for l in B)
+                # slot offsets are relative to the body's own row, so they advance after every body (grouped staging: relative to the
+                # group's first row; they advance by U rows after the group)
+                for (d, c), nm in sorted(self.slotvars.items()):
+                    if not self.grouped:
+                        E(ind + f"{nm} += RW; if ({nm} == {d} * RW) {nm} = 0;")
+                if self.bulk:
+                    E(ind + f"++it; if (++bar_i == {self.NBAR}) bar_i = 0; if (++bar_w == {self.NBAR}) {{ bar_w = 0; bar_wp ^= 1; }}")
+                if wrap:
+                    E(f"{ind0}}}")
+        if steady_bodies:
+            E(f"    if (j >= r0 && j + {self.U - 1 + self.PF} < r1) {{   // steady group: every row is stored, every staged row is needed")
+            emit_bodies(steady_bodies, False, "      ")
+            E("    } else {   // the first and the last rows of a chunk: each row behind its tests")
+            emit_bodies(bodies, True, "      ")
+            E("    }")
+        else:
+            emit_bodies(bodies, True, "    ")
         if self.grouped:
             for (d, c), nm in sorted(self.slotvars.items()):
                 E(f"    {nm} += {self.U} * RW; if ({nm} >= {d} * RW) {nm} -= {d} * RW;")
@@ -871,6 +888,12 @@ class StageEmitter:
             P("const bool edge_x = g.cyc_x && (strip_lo < g.xorg + g.gx_hi || strip_lo + W_OUT > g.xorg + g.nx - g.gx_lo);")
             P("const bool edge_y = g.wrap_y_local && (r0 < g.yorg + g.gy_hi || r1 > g.yorg + g.nyl - g.gy_lo);")
             P("const bool edge_any = edge_x || edge_y;   // this CTA writes cells that have a ghost copy")
+        # vector stages of rank-1 / rank-2 machines: the full-vector store and accumulate are predicated on li_all; partial vectors at the
+        # strip's edge and cells with a ghost copy go through ONE rarely taken block per row instead of a branch per store and reduce
+        compact = Z == 1 and V > 1 and all(VEC_TYPE.get((self.T(v), V)) for (_s, v) in st.store_targets)
+        if compact:
+            P("const bool rare = (li_any && !li_all)" + (" || edge_any" if cyclic else "") + ";   // this thread has more to do than one full-vector store per row")
+        rare_lines: List[str] = []
         B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
         B.append(f"  const int row = {row_expr};")
         lines, res = self.scope_guarded(targets, 0)
@@ -916,8 +939,23 @@ class StageEmitter:
             on = [oname(v, zo, k) for k in range(V)]
             P(f"{T}* __restrict__ {ps} = {self.outp(s, T)} + (ptrdiff_t)r0 * g.pitch + tc" + (f" + (ptrdiff_t){zo} * g.plane" if zo else "") +
               ";   // advances one row per output row")
-            B.append(f"  {{ {T}* __restrict__ p = {ps}; {ps} += g.pitch;" + (f" if ({zlive(zo)}) {{" if zo else ""))
-            if vt:
+            dst = B
+            if compact:
+                mk = f"make_{vt}({', '.join(on)})"
+                st_fn = {"cs": "__stcs(reinterpret_cast<%s*>(p), %s)", "cg": "__stcg(reinterpret_cast<%s*>(p), %s)"}.get(
+                    self.tuning.store_hint, "*reinterpret_cast<%s*>(p) = %s") % (vt, mk)
+                B.append(f"  {{ {T}* __restrict__ p = {ps}; {ps} += g.pitch; if (li_all) {{ {st_fn}; }} }}")
+                dst = rare_lines
+                dst.append(f"  {{ {T}* __restrict__ p = {ps} - g.pitch;")
+                dst.append("    if (!li_all) {")
+                for k in range(V):
+                    dst.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
+                dst.append("    }")
+            else:
+                B.append(f"  {{ {T}* __restrict__ p = {ps}; {ps} += g.pitch;" + (f" if ({zlive(zo)}) {{" if zo else ""))
+            if compact:
+                pass
+            elif vt:
                 mk = f"make_{vt}({', '.join(on)})"
                 if self.tuning.store_hint == "cs":      # streaming store (evict-first): the row is not read again before the next step
                     B.append(f"    if (li_all) {{ __stcs(reinterpret_cast<{vt}*>(p), {mk}); }}")
@@ -937,19 +975,21 @@ class StageEmitter:
             # fused ghost-cell writes for Cyclic axes: the wrap the reference evaluates with % on every
             # read (PlanTrans.hs:477-484) is materialised once per written cell
             if cyclic:
-                B.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
+                dst.append("    if (edge_any) { if (li_any && (edge_x || row < g.yorg + g.gy_hi || row >= g.yorg + g.nyl - g.gy_lo)) {")
                 for k in range(V):
-                    B.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
-                    B.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
-                    B.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
-                    B.append(f"        if (dc) p[{k} + dc] = {on[k]};")
-                    B.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = {on[k]};")
-                    B.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = {on[k]};")
-                    B.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]};   // domain narrower than the ghost width")
-                    B.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = {on[k]};")
-                    B.append("      }")
-                B.append("    } }")
-            B.append("  }" + ("}" if zo else ""))
+                    dst.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) {{ const int c = tc + {k} - g.xorg; const int r = row - g.yorg;")
+                    dst.append("        const int dc = !g.cyc_x ? 0 : (c < g.gx_hi ? g.nx : (c >= g.nx - g.gx_lo ? -g.nx : 0));")
+                    dst.append("        const int dr = !g.wrap_y_local ? 0 : (r < g.gy_hi ? g.nyl : (r >= g.nyl - g.gy_lo ? -g.nyl : 0));")
+                    dst.append(f"        if (dc) p[{k} + dc] = {on[k]};")
+                    dst.append(f"        if (dr) p[{k} + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                    dst.append(f"        if (dc && dr) p[{k} + dc + (ptrdiff_t)dr * g.pitch] = {on[k]};")
+                    dst.append(f"        if (g.cyc_x && c < g.gx_hi && c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]};   // domain narrower than the ghost width")
+                    dst.append(f"        if (g.wrap_y_local && r < g.gy_hi && r >= g.nyl - g.gy_lo) p[{k} - (ptrdiff_t)g.nyl * g.pitch] = {on[k]};")
+                    dst.append("      }")
+                dst.append("    } }")
+            dst.append("  }" + ("}" if zo else ""))
+        carried_now = [False]     # the carried scope's values live in its own block: it keeps the plain form
+
         def accumulate(v, rop, slot, names, ind):
             cls = {"Sum": "OmSum", "Min": "OmMin", "Max": "OmMax"}[rop]
             chain = f"acc{slot}"
@@ -957,6 +997,13 @@ class StageEmitter:
                 chain = f"{cls}::op({chain}, {names[k]})"
             if V == 1:
                 B.append(f"{ind}if (li_any) {{ acc{slot} = {chain}; }}")
+                return
+            if compact and not carried_now[0]:
+                B.append(f"{ind}if (li_all) {{ acc{slot} = {chain}; }}")
+                rare_lines.append("  if (!li_all) {")
+                for k in range(V):
+                    rare_lines.append(f"    if (tc + {k} >= out_lo && tc + {k} < out_hi) acc{slot} = {cls}::op(acc{slot}, {names[k]});")
+                rare_lines.append("  }")
                 return
             B.append(f"{ind}if (li_all) {{ acc{slot} = {chain}; }}")
             B.append(f"{ind}else if (li_any) {{")
@@ -970,7 +1017,12 @@ class StageEmitter:
             accumulate(v, rop, slot, [oname(v, zo, k) for k in range(V)], "    " if zo else "  ")
             if zo:
                 B.append("  }")
+        if rare_lines:
+            B.append("  if (rare) {   // partial vectors at the strip's edge, cells with a ghost copy")
+            B += ["  " + l for l in rare_lines]
+            B.append("  }")
         if st.carried:
+            carried_now[0] = True
             # the level-0 reduce of the NEXT call of this kernel, evaluated on the values just stored (schedule.find_carry)
             B.append("  {   // carried reduce: next call's level-0 stage becomes an 8-byte copy")
             lines, res = self.scope_guarded([v for (v, _o, _k) in st.carried], 0, tag="c")

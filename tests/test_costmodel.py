@@ -50,5 +50,5 @@ def test_estimate_of_the_built_hydro_library():
     desc, so = build_hydro(fast=True, verbose=True)
     e = costmodel.estimate_stage(desc, so, size=(4096, 4096))
     assert e.symbol == "om_Hydro_proceed_stage1" and e.threads == 128 and e.ctas_per_sm == 3
-    assert 1500 < e.instructions < 2000 and 600 < e.fp64 < 800 and e.local == 0
-    assert 0.9 < e.ms / 1.18 < 1.2                           # measured kernel time: 1.18 ms (profiles/r1i_bench_hydro_fast.json)
+    assert 1300 < e.instructions < 1700 and 600 < e.fp64 < 800 and e.local == 0      # round 2: 1 469 (716) after the ghost-write code left
+    assert 0.85 < e.ms / 1.15 < 1.2                          # measured kernel time: 1.15-1.16 ms (profiles/r2s_bench_n1.json)

@@ -14,30 +14,41 @@ from paraiso_b200.examples.life import life_om, life_setup  # noqa: E402
 from paraiso_b200.runtime import Machine  # noqa: E402
 
 size = (16384, 16384)
-seed = torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory()
+seed = None
+
+
+def variant_setups():
+    a = life_setup("master")
+    b = life_setup("master")
+    b.tuning.peel_fill = False
+    c = life_setup("master")
+    c.tuning.barrier_group = True
+    return [("default (steady-state copy of the row loop)", None, a), ("one row loop, every row behind its tests", "Life_CC_tested", b),
+            ("barrier per group of rows", "Life_CC_grouped", c)]
 
 
 def variants():
-    """(label, machine): the default build and the one with a CTA barrier per row (Tuning.barrier_group = False)."""
-    yield "barrier per group", life_machine(size)
-    s = life_setup("master")
-    s.tuning.barrier_group = False
-    desc, so = build_machine(s, life_om("master"), tag="Life_CC_rowbarrier")
-    yield "barrier per row", Machine(desc, so, size=size)
+    for label, tag, s in variant_setups():
+        if tag is None:
+            yield label, life_machine(size)
+        else:
+            desc, so = build_machine(s, life_om("master"), tag=tag)
+            yield label, Machine(desc, so, size=size)
 
 
 if __name__ == "__main__":
     if "--prebuild" in sys.argv:
-        s = life_setup("master")
-        s.tuning.barrier_group = False
-        build_machine(s, life_om("master"), tag="Life_CC_rowbarrier")
+        for _label, tag, s in variant_setups():
+            if tag:
+                build_machine(s, life_om("master"), tag=tag)
         sys.exit(0)
+    seed = torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory()
     for label, m in variants():
         m.call("init")
         m.set_from_host("cell", seed)
         st = m.kernels["proceed"]["stages"][0]
         occ = getattr(m.lib, st["symbol"] + "_occupancy")()
-        for chunks in [0, 444, 512, 541, 582, 624, 656, 666, 707, 749, 790, 832, 874, 915, 1000, 1332]:
+        for chunks in [0, 541, 656, 749, 790, 832, 874, 915, 1000]:
             m.force_chunks = chunks
             m._geom_cache.clear()
             ms = min(measure(m, "proceed", steps=20, stage=0) for _ in range(3))
