@@ -77,3 +77,22 @@ def test_reference_driver_compiles_and_links_unchanged(name, tag, driver, tmp_pa
            f"-Wl,-rpath,{d}", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_graph_capture_and_host_pipeline_need_a_cuda_device():
+    """Machine.capture / hostio.HostPipeline are CUDA-only plumbing: on an emulated (CPU) machine they refuse instead of degrading."""
+    import torch
+    from paraiso_b200.examples.life import life_om, life_setup
+    from paraiso_b200.runtime import Machine
+    from tests.emu.build_emu import build_emulated
+    desc, so = build_emulated(life_setup("master", size=(64, 48)), life_om("master"), tag="Life_ring_1_cp_async")
+    m = Machine(desc, so, size=(64, 48), device="cpu", _emulated=True)
+    with pytest.raises(ValueError):
+        m.capture("proceed", 3)                       # odd: the buffers would not be back in place
+    with pytest.raises(RuntimeError):
+        m.capture("proceed", 2)                       # no CUDA device
+    assert m.slow_path_cells() == 0 and m.early_exchanges == 0
+    if not torch.cuda.is_available():
+        from paraiso_b200.hostio import HostPipeline
+        with pytest.raises(Exception):
+            HostPipeline(m, "proceed", ["cell"])
