@@ -241,6 +241,7 @@ class Machine:
             # whole waves of resident CTAs (sms * occ) when that moves it by less than 8 % (Life 16384^2: 819 -> 832 chunks =
             # 20.0 waves).  Measured, the kernel is NOT wave-quantised — flat within 1.5 % from 13 to 24 waves
             # (profiles/r2o_life_chunks.jsonl) — so this only keeps the grid regular; the height itself is what matters
+            chunks = max(1, nrows // st["chunk_rows"])
             wave = sms * occ
             k = max(1, round(strips * chunks * layers / wave))
             whole = (k * wave) // (strips * layers)
