@@ -21,6 +21,7 @@ the reference's C++.
 """
 from __future__ import annotations
 
+import re
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -892,7 +893,11 @@ class StageEmitter:
         # strip's edge and cells with a ghost copy go through ONE rarely taken block per row instead of a branch per store and reduce
         compact = Z == 1 and V > 1 and all(VEC_TYPE.get((self.T(v), V)) for (_s, v) in st.store_targets)
         if compact:
-            P("const bool rare = (li_any && !li_all)" + (" || edge_any" if cyclic else "") + ";   // this thread has more to do than one full-vector store per row")
+            if cyclic:
+                # (in a strip at the x edge only the vectors that hold a column with a ghost copy take the block — one warp of the CTA,
+                #  not all of them: 2 of Life 16384^2's 32 strips are edge strips)
+                P("const bool ghost_x = edge_x && li_any && (tc - g.xorg < g.gx_hi || tc + V - g.xorg > g.nx - g.gx_lo);")
+            P("const bool rare = (li_any && !li_all)" + (" || edge_y || ghost_x" if cyclic else "") + ";   // this thread has more to do than one full-vector store per row")
         rare_lines: List[str] = []
         B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
         B.append(f"  const int row = {row_expr};")
@@ -1017,7 +1022,28 @@ class StageEmitter:
             accumulate(v, rop, slot, [oname(v, zo, k) for k in range(V)], "    " if zo else "  ")
             if zo:
                 B.append("  }")
-        if rare_lines:
+        if rare_lines and self.tuning.cold_rare:
+            # the block as a function of its own (a noinline closure that captures what it reads by value and returns the accumulators):
+            # inline, ptxas lays its ~100 instructions per vector lane out in the middle of every row body, and the hot path of a
+            # row is two short runs with a 5 KB jump between them (Life: a 38 KB loop of which 8 KB execute)
+            slots = sorted({int(m) for l in rare_lines for m in re.findall(r"\bacc(\d+)\b", l)})
+            styp = {slot: self.T(v) for (v, _rop, slot) in self.st.reduce_targets + self.st.carried}
+            body = [re.sub(r"\bacc(\d+)\b", lambda m: f"om_a.s{m.group(1)}", l) for l in rare_lines]
+            B.append("  if (rare) {   // (cold) partial vectors at the strip's edge, cells with a ghost copy")
+            if slots:
+                B.append("    struct OmRare { " + " ".join(f"{styp[s_]} s{s_};" for s_ in slots) + " };")
+                B.append("    const OmRare om_rr = [=]() __attribute__((noinline)) -> OmRare {")
+                B.append("      OmRare om_a; " + " ".join(f"om_a.s{s_} = acc{s_};" for s_ in slots))
+                B += ["    " + l for l in body]
+                B.append("      return om_a;")
+                B.append("    }();")
+                B.append("    " + " ".join(f"acc{s_} = om_rr.s{s_};" for s_ in slots))
+            else:
+                B.append("    [=]() __attribute__((noinline)) {")
+                B += ["    " + l for l in body]
+                B.append("    }();")
+            B.append("  }")
+        elif rare_lines:
             B.append("  if (rare) {   // partial vectors at the strip's edge, cells with a ghost copy")
             B += ["  " + l for l in rare_lines]
             B.append("  }")

@@ -29,6 +29,17 @@ __global__ void sqrt_kernel(const double* x, double* ours, double* ieee, unsigne
   if (flag) atomicOr(bad, 1u);
   if (nslow) atomicAdd(bad + 1, nslow);
 }
+// the fast_math build's division / square root (om_frcp + om_fdiv_r, om_fsqrt): not IEEE, checked for their error bound
+__global__ void fast_kernel(const double* a, const double* b, double* quot, double* root, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    quot[i] = om_fdiv_r(a[i], b[i], om_frcp(b[i]));
+    root[i] = om_fsqrt(a[i]);
+  }
+}
+extern "C" int om_check_fast(const void* a, const void* b, void* quot, void* root, long long n, void* stream) {
+  fast_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const double*)a, (const double*)b, (double*)quot, (double*)root, n);
+  return (int)cudaGetLastError();
+}
 extern "C" int om_check_div(const void* a, const void* b, void* ours, void* ieee, void* bad, long long n, void* stream) {
   div_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const double*)a, (const double*)b, (double*)ours, (double*)ieee, (unsigned*)bad, n);
   return (int)cudaGetLastError();

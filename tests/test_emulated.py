@@ -15,17 +15,19 @@ from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
 
-def _life(size, steps, mode, window=True, staging="cp_async"):
+def _life(size, steps, mode, window=True, staging="cp_async", cold=False):
     setup = life_setup("master", size=size)
     setup.tuning.skeleton = mode
     setup.tuning.row_window = window
     setup.tuning.staging = staging
-    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}")
+    setup.tuning.cold_rare = cold
+    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}" + ("_cold" if cold else ""))
     with open(os.path.join(os.path.dirname(so), "Life_kernels.cu")) as f:
         src = f.read()
     assert ("register streaming" in src) == (mode == "stream")
     assert ("stencil window (rotates by renaming)" in src) == (mode == "ring" and window)
     assert ("om_bulk_g2s" in src) == (staging == "bulk")
+    assert ("const OmRare om_rr = [=]() __attribute__((noinline))" in src) == cold
     m = Machine(desc, so, size=size, device="cpu", _emulated=True)
     o = OracleMachine(life_setup("master", size=size), life_om("master"))
     init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
@@ -42,6 +44,12 @@ def _life(size, steps, mode, window=True, staging="cp_async"):
 def test_life_ring_skeleton(size):
     """(includes domains narrower than the ghost width: every neighbour of a 1x1 Cyclic grid is the cell itself)"""
     _life(size, 4, "ring")
+
+
+@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37), (1, 1), (2, 2), (1, 7), (7, 1)])
+def test_life_with_the_rare_block_out_of_line(size):
+    """Tuning.cold_rare: partial vectors and ghost copies of a row go through a noinline closure that returns the accumulators."""
+    _life(size, 4, "ring", cold=True)
 
 
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])

@@ -136,6 +136,38 @@ def test_tiny_operands_raise_the_slow_flag_and_specials_the_state_guard(lib):
     assert 0 < nslow < a.numel()
 
 
+def test_fast_math_division_and_sqrt_stay_within_their_error_bound(lib):
+    """The fast_math build's sequences (om_frcp + om_fdiv_r, om_fsqrt) are not IEEE: the reciprocal is within 1 ulp, a quotient
+    within 2 ulp, a square root within 1 ulp of the correctly rounded value on 2^26 random operands; sqrt(0) is exactly 0."""
+    import torch
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    n = 1 << 24
+    worst_q = worst_r = 0
+    for it in range(4):
+        span = 250 if it < 2 else 2
+        a = _random_doubles(torch, n, gen, -span, span, signed=False)
+        b = _random_doubles(torch, n, gen, -span, span)
+        quot, root = torch.empty_like(a), torch.empty_like(a)
+        rc = lib.om_check_fast(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(quot.data_ptr()),
+                               ctypes.c_void_p(root.data_ptr()), ctypes.c_longlong(n), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        # same sign and both normal: the distance in ulps is the difference of the bit patterns
+        worst_q = max(worst_q, int((quot.view(torch.int64) - (a / b).view(torch.int64)).abs().max().item()))
+        worst_r = max(worst_r, int((root.view(torch.int64) - torch.sqrt(a).view(torch.int64)).abs().max().item()))
+    assert worst_q <= 2 and worst_r <= 1, (worst_q, worst_r)
+    # zero radicands / numerators (Hydro: velocity1 == 0), perfect squares, a radicand below the 1e-284 the seed's offset is exact for
+    k = torch.arange(0, 1 << 16, device="cuda", dtype=torch.float64)
+    x = torch.cat([k * k, torch.zeros(8, dtype=torch.float64, device="cuda"), torch.full((8,), 1e-290, dtype=torch.float64, device="cuda")]).contiguous()
+    b = torch.full_like(x, 3.0)
+    quot, root = torch.empty_like(x), torch.empty_like(x)
+    assert lib.om_check_fast(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(quot.data_ptr()),
+                             ctypes.c_void_p(root.data_ptr()), ctypes.c_longlong(x.numel()), None) == 0
+    torch.cuda.synchronize()
+    assert bool((root[: 1 << 16] == k).all()) and bool((root[1 << 16: (1 << 16) + 8] == 0).all()) and bool((quot[(1 << 16): (1 << 16) + 8] == 0).all())
+    assert float((root[-8:] / 1e-145 - 1).abs().max()) < 1e-9
+
+
 def test_exact_build_raises_when_the_state_leaves_the_normal_range():
     """Machine level: a NaN that reaches the stored state surfaces as a RuntimeError at the next host read; denormal
     velocities do not — those cells take the IEEE slow path and the state stays bit-identical to the oracle's."""
