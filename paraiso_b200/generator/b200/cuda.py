@@ -897,8 +897,10 @@ class StageEmitter:
                 # (in a strip at the x edge only the vectors that hold a column with a ghost copy take the block — one warp of the CTA,
                 #  not all of them: 2 of Life 16384^2's 32 strips are edge strips)
                 P("const bool ghost_x = edge_x && li_any && (tc - g.xorg < g.gx_hi || tc + V - g.xorg > g.nx - g.gx_lo);")
+                P("const bool ghost_only = ghost_x && li_all && !edge_y;   // ... and nothing else to do: the lean form of the block")
             P("const bool rare = (li_any && !li_all)" + (" || edge_y || ghost_x" if cyclic else "") + ";   // this thread has more to do than one full-vector store per row")
         rare_lines: List[str] = []
+        lean_lines: List[str] = []     # the same block for a whole vector inside the strip whose only extra work is the x ghost copy
         B.append(f"if ({guard}) {{   // OUT: stores and reduce accumulation for one row")
         B.append(f"  const int row = {row_expr};")
         lines, res = self.scope_guarded(targets, 0)
@@ -952,6 +954,11 @@ class StageEmitter:
                 B.append(f"  {{ {T}* __restrict__ p = {ps}; {ps} += g.pitch; if (li_all) {{ {st_fn}; }} }}")
                 dst = rare_lines
                 dst.append(f"  {{ {T}* __restrict__ p = {ps} - g.pitch;")
+                if cyclic:
+                    lean_lines.append(f"  {{ {T}* __restrict__ p = {ps} - g.pitch;")
+                    for k in range(V):
+                        lean_lines.append(f"    {{ const int c = tc + {k} - g.xorg; if (c < g.gx_hi) p[{k} + g.nx] = {on[k]}; if (c >= g.nx - g.gx_lo) p[{k} - g.nx] = {on[k]}; }}")
+                    lean_lines.append("  }")
                 dst.append("    if (!li_all) {")
                 for k in range(V):
                     dst.append(f"      if (tc + {k} >= out_lo && tc + {k} < out_hi) p[{k}] = {on[k]};")
@@ -1042,6 +1049,16 @@ class StageEmitter:
                 B.append("    [=]() __attribute__((noinline)) {")
                 B += ["    " + l for l in body]
                 B.append("    }();")
+            B.append("  }")
+        elif rare_lines and lean_lines:
+            # an edge strip's ghost column is written on every row by one warp of the CTA, and the CTA waits for it at the row's
+            # barrier: that warp gets 4 compare + store pairs per vector instead of the general block's ~300 instructions
+            B.append("  if (rare) {   // partial vectors at the strip's edge, cells with a ghost copy")
+            B.append("    if (ghost_only) {   // a whole vector whose only extra is the ghost copy across x")
+            B += ["    " + l for l in lean_lines]
+            B.append("    } else {")
+            B += ["    " + l for l in rare_lines]
+            B.append("    }")
             B.append("  }")
         elif rare_lines:
             B.append("  if (rare) {   // partial vectors at the strip's edge, cells with a ghost copy")

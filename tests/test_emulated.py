@@ -40,9 +40,10 @@ def _life(size, steps, mode, window=True, staging="cp_async", cold=False):
     assert int(m.scalar("generation")) == steps
 
 
-@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37), (1, 1), (2, 2), (1, 7), (7, 1)])
+@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37), (1, 1), (2, 2), (1, 7), (7, 1), (80, 100), (4, 90), (600, 130)])
 def test_life_ring_skeleton(size):
-    """(includes domains narrower than the ghost width: every neighbour of a 1x1 Cyclic grid is the cell itself)"""
+    """(includes domains narrower than the ghost width: every neighbour of a 1x1 Cyclic grid is the cell itself; the tall ones
+    have chunks without a y wrap, where the edge strips' ghost columns go through the lean form of the rare block)"""
     _life(size, 4, "ring")
 
 

@@ -12,14 +12,24 @@ from paraiso_b200.examples.life import life_om, life_setup  # noqa: E402
 size = (16384, 16384)
 if __name__ == "__main__":
     built = []
+    gen = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "paraiso_b200", "_generated")
+    for name, d in (("before ghost_x", "variant_Life_old"), ("ghost_x, general block only", "variant_Life_ghostx")):   # kept libraries of earlier generators
+        if os.path.exists(os.path.join(gen, d, "libom_Life.so")):
+            with open(os.path.join(gen, d, "Life_abi.json")) as f:
+                built.append((name, (json.load(f), os.path.join(gen, d, "libom_Life.so"))))
     for cold in (False, True):
         s = life_setup("master")
         s.tuning.cold_rare = cold
-        built.append((f"cold_rare={cold}", build_machine(s, life_om("master"), tag=f"variant_Life_cold{int(cold)}", verbose=True)))
-    old = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "paraiso_b200", "_generated", "variant_Life_old")
-    if os.path.exists(os.path.join(old, "libom_Life.so")):
-        with open(os.path.join(old, "Life_abi.json")) as f:
-            built.insert(0, ("before ghost_x", (json.load(f), os.path.join(old, "libom_Life.so"))))
+        built.append((f"lean ghost block, cold_rare={cold}", build_machine(s, life_om("master"), tag=f"variant_Life_cold{int(cold)}", verbose=True)))
+    # timing bound only (wrong ghost columns): no thread of an edge strip takes the block for its ghost copy
+    from paraiso_b200.build import compile_kernels, generate_to
+    s = life_setup("master")
+    desc, d = generate_to(s, life_om("master"), tag="variant_Life_noghost")
+    with open(os.path.join(d, "Life_kernels.cu")) as f:
+        src = f.read()
+    with open(os.path.join(d, "Life_kernels.cu"), "w") as f:
+        f.write(src.replace("const bool ghost_x = edge_x &&", "const bool ghost_x = false &&"))
+    built.append(("no x ghost copies (bound, wrong result)", (desc, compile_kernels(d, desc["name"], verbose=True))))
     if "--prebuild" in sys.argv:
         sys.exit(0)
     import numpy as np
