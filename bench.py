@@ -225,10 +225,10 @@ def measured_traffic(m, symbol: str, tag: str):
         e = json.load(f).get(symbol + tag)
     if not e:
         return None
-    cu = os.path.join(os.path.dirname(m.lib._name), f"{m.name}_kernels.cu")
-    try:
-        with open(cu, "rb") as f:
-            h = hashlib.sha1(f.read()).hexdigest()[:16]
+    d = os.path.dirname(m.lib._name)
+    try:      # the generated kernels and the runtime header they include (its device functions are part of the kernel's code)
+        with open(os.path.join(d, f"{m.name}_kernels.cu"), "rb") as f, open(os.path.join(d, "om_runtime.cuh"), "rb") as r:
+            h = hashlib.sha1(f.read() + r.read()).hexdigest()[:16]
     except OSError:
         return None
     return e.get("dram_bytes_per_launch") if e.get("kernel_source_sha1_16") == h else None

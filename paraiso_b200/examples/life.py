@@ -73,9 +73,12 @@ def life_setup(variant: str = "master", size=None) -> Setup:
         s = Setup(local_size=size or (80, 48), boundary=(CYCLIC, CYCLIC), directory="./dist/")
     else:
         s = Setup(local_size=size or (128, 128), boundary=(OPEN, OPEN), directory="./dist/")  # LifeMain.hs:121-125
-    # winners of the sweeps in profiles/r1_life_sweep.txt: three rows in flight per CTA; chunk height re-swept in round 2 with
-    # balanced chunks (profiles/r2o_life_chunks.jsonl: 832 chunks of 19.7 rows = 20 waves of CTAs, 0.3548 ms; 656 of 25: 0.3602)
-    s.tuning.prefetch_rows = 3
-    s.tuning.chunk_rows_light = 20
+    # rows in flight per CTA and chunk height, re-swept whenever the kernel changed: round 1 (profiles/r1_life_sweep.txt) 3 rows;
+    # round 2 with balanced chunks (r2o_life_chunks.jsonl) 3 rows, 20-row chunks; after the lean ghost block took the kernel from
+    # issue-bound to latency-bound (ALU pipe 75 % -> 67 %), deeper staging and shorter chunks pay (r2ag / r2ah_life_pf.jsonl, same box:
+    # 3 rows / 20-row chunks 0.3512 ms, 6 / 20 0.3470, 4 / 16 0.3455, 6 / 16 0.3425, 6 / 14 0.3451, 6 / 12 0.3540): 1040 chunks of
+    # 15.75 rows = 25 waves of CTAs, 6 x 2 KB rows in flight per CTA
+    s.tuning.prefetch_rows = 6
+    s.tuning.chunk_rows_light = 16
     s.tuning.min_blocks = 9          # 9 CTAs of 128 threads per SM: at most 56 registers (the steady-state copy of the row loop asks for 60)
     return s

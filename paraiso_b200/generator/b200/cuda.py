@@ -123,6 +123,8 @@ class StageEmitter:
         self.newton = (not self.fast) and self.tuning.exact_divsqrt == "newton"   # branch-free IEEE-correct Double division / sqrt
         self.uses_range_flag = False
         self._steady = False          # emitting the steady-state copy of a row-window body (no start / end tests)
+        self._clean = False           # ... for a CTA without partial vectors or ghost copies (no rarely taken block)
+        self.has_rare = False         # some row body has a rarely taken block
         self._ieee_scope = False      # emitting the cold clone of a scope: the compiler's own IEEE division / sqrt
         self._guarded_ops = 0         # guarded divisions / square roots emitted by the scope() call in progress
         self.PF = self.tuning.prefetch_rows     # cp.async prefetch distance in rows
@@ -626,13 +628,17 @@ class StageEmitter:
                 stage_row(group_top, self.U + u, f"j + {self.U + u} < r1", "")
             group_top.append("om_cp_async_commit();")
         steady_bodies: List[List[str]] = []
+        clean_bodies: List[List[str]] = []
         if self.window:
             # one unrolled body per window row: the register sets rotate by renaming
             wregs: Dict[str, str] = {}
-            for u in list(range(self.U)) * (2 if (self.tuning.peel_fill and not self.grouped) else 1):
+            peel = self.tuning.peel_fill and not self.grouped
+            for u in list(range(self.U)) * ((3 if self.tuning.clean_ctas else 2) if peel else 1):
                 # (second pass: the steady-state copies — every row of the group is stored and every staged row is needed, so the
-                #  per-row tests go and a group is tested once, CTA-uniformly)
+                #  per-row tests go and a group is tested once, CTA-uniformly; third pass: the same for a CTA none of whose threads
+                #  ever takes the rarely taken block of a row — it is not emitted at all)
                 self._steady = len(bodies) == self.U
+                self._clean = self._steady and len(steady_bodies) == self.U
                 self.window_u = u
                 B: List[str] = []
                 if not self.grouped:
@@ -656,8 +662,8 @@ class StageEmitter:
                     for o in list(range(-i.rd_xlo, 0)) + list(range(V, V + i.rd_xhi)):
                         B.append(f"w{b}_{sset}_{_m(o)} = ring{b}[{so} + tb + ({o})];")
                 B += self.emit_out(row_expr=f"j + {u}", guard="true" if self._steady else f"j + {u} >= r0")
-                (steady_bodies if self._steady else bodies).append(B)
-            self._steady = False
+                (clean_bodies if self._clean else steady_bodies if self._steady else bodies).append(B)
+            self._steady = self._clean = False
             self.window_u = None
             self.wregs = wregs
         else:
@@ -779,6 +785,8 @@ class StageEmitter:
                 E(f"  {T} " + ", ".join(f"{n_} = 0" for n_ in sorted(ns)) + ";   // stencil window (rotates by renaming)")
         for l in self.post_init:
             E("  " + l)
+        if clean_bodies and self.has_rare:
+            E("  const bool cta_rare = __syncthreads_or(rare);   // CTA-uniform: an edge strip, a chunk with a y wrap, a strip with partial vectors")
         nb_ = len(bodies)
         if not self.window and fill_body is not None:
             E("  int j = jbeg;")
@@ -810,7 +818,14 @@ class StageEmitter:
                     E(f"{ind0}}}")
         if steady_bodies:
             E(f"    if (j >= r0 && j + {self.U - 1 + self.PF} < r1) {{   // steady group: every row is stored, every staged row is needed")
-            emit_bodies(steady_bodies, False, "      ")
+            if clean_bodies and self.has_rare:
+                E("      if (!cta_rare) {   // no thread of this CTA has a partial vector or a ghost copy: the row bodies without that block")
+                emit_bodies(clean_bodies, False, "        ")
+                E("      } else {")
+                emit_bodies(steady_bodies, False, "        ")
+                E("      }")
+            else:
+                emit_bodies(steady_bodies, False, "      ")
             E("    } else {   // the first and the last rows of a chunk: each row behind its tests")
             emit_bodies(bodies, True, "      ")
             E("    }")
@@ -1029,6 +1044,10 @@ class StageEmitter:
             accumulate(v, rop, slot, [oname(v, zo, k) for k in range(V)], "    " if zo else "  ")
             if zo:
                 B.append("  }")
+        if rare_lines:
+            self.has_rare = True
+        if self._clean:
+            rare_lines = []
         if rare_lines and self.tuning.cold_rare:
             # the block as a function of its own (a noinline closure that captures what it reads by value and returns the accumulators):
             # inline, ptxas lays its ~100 instructions per vector lane out in the middle of every row body, and the hot path of a

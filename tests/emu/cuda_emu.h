@@ -66,10 +66,20 @@ struct EmuBlock {
   std::barrier<>* bar;
   std::vector<std::barrier<>*> warp_bar;
   unsigned char xchg[64][32][8];
+  unsigned vote = 0;
 };
 static EmuBlock* emu_block;
 
 static inline void __syncthreads() { emu_block->bar->arrive_and_wait(); }
+static inline int __syncthreads_or(int pred) {
+  if (pred) __atomic_fetch_or(&emu_block->vote, 1u, __ATOMIC_SEQ_CST);
+  emu_block->bar->arrive_and_wait();
+  const int r = __atomic_load_n(&emu_block->vote, __ATOMIC_SEQ_CST) != 0;
+  emu_block->bar->arrive_and_wait();      // everybody has read the vote ...
+  if (threadIdx.x == 0) emu_block->vote = 0;   // ... before it is cleared for the next one
+  emu_block->bar->arrive_and_wait();
+  return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }

@@ -62,3 +62,19 @@ def test_gpu_arm_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     r = _bench("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_traffic_stamps_belong_to_the_committed_kernel_sources():
+    """`roofline.traffic` is reported only while the ncu capture's source hash matches the loaded kernel: the committed table must
+    match the committed generated sources (a kernel change without a new capture turns the field into null, not into a stale number)."""
+    import hashlib
+    gen = os.path.join(ROOT, "paraiso_b200", "_generated")
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        table = json.load(f)
+    for key, d, name in (("om_Life_proceed_stage0", "Life_CC", "Life"), ("om_Hydro_proceed_stage1_fast", "Hydro_OO_Double_fast", "Hydro"),
+                         ("om_Hydro_proceed_stage1_exact", "Hydro_OO_Double", "Hydro")):
+        with open(os.path.join(gen, d, f"{name}_kernels.cu"), "rb") as f, open(os.path.join(gen, d, "om_runtime.cuh"), "rb") as r:
+            h = hashlib.sha1(f.read() + r.read()).hexdigest()[:16]
+        assert table[key]["kernel_source_sha1_16"] == h, key
+        assert 0.95 < table[key]["ratio"] < 1.1            # DRAM traffic = algorithmic bytes: nothing is read twice
+        assert os.path.exists(os.path.join(ROOT, table[key]["source"]))

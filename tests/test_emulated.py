@@ -15,19 +15,21 @@ from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
 
-def _life(size, steps, mode, window=True, staging="cp_async", cold=False):
+def _life(size, steps, mode, window=True, staging="cp_async", cold=False, clean=False):
     setup = life_setup("master", size=size)
     setup.tuning.skeleton = mode
     setup.tuning.row_window = window
     setup.tuning.staging = staging
     setup.tuning.cold_rare = cold
-    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}" + ("_cold" if cold else ""))
+    setup.tuning.clean_ctas = clean
+    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}" + ("_cold" if cold else "") + ("_clean" if clean else ""))
     with open(os.path.join(os.path.dirname(so), "Life_kernels.cu")) as f:
         src = f.read()
     assert ("register streaming" in src) == (mode == "stream")
     assert ("stencil window (rotates by renaming)" in src) == (mode == "ring" and window)
     assert ("om_bulk_g2s" in src) == (staging == "bulk")
     assert ("const OmRare om_rr = [=]() __attribute__((noinline))" in src) == cold
+    assert ("const bool cta_rare = __syncthreads_or(rare);" in src) == clean
     m = Machine(desc, so, size=size, device="cpu", _emulated=True)
     o = OracleMachine(life_setup("master", size=size), life_om("master"))
     init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
@@ -51,6 +53,13 @@ def test_life_ring_skeleton(size):
 def test_life_with_the_rare_block_out_of_line(size):
     """Tuning.cold_rare: partial vectors and ghost copies of a row go through a noinline closure that returns the accumulators."""
     _life(size, 4, "ring", cold=True)
+
+
+@pytest.mark.parametrize("size", [(80, 48), (1600, 70), (2, 2)])
+def test_life_with_row_bodies_for_ctas_without_a_rare_block(size):
+    """Tuning.clean_ctas: CTAs that are neither an edge strip nor a chunk with a y wrap (the 1600-wide grid has them) run copies of
+    the row bodies without the rarely taken block."""
+    _life(size, 4, "ring", clean=True)
 
 
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])

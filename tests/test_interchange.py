@@ -125,7 +125,7 @@ def test_command_line_front_end_from_dump_and_cpp(tmp_path):
     out = tmp_path / "dist-b200"
     cmd = [sys.executable, os.path.join(root, "tools", "om2b200.py"), str(tmp_path / "OM.txt"), "--cpp",
            str(tmp_path / "Life.cpp"), "--size", "128x128", "--boundary", "open,open", "--out", str(out),
-           "--tune", "prefetch_rows=3", "--tune", "chunk_rows_light=20", "--tune", "min_blocks=9"]
+           "--tune", "prefetch_rows=6", "--tune", "chunk_rows_light=16", "--tune", "min_blocks=9"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     tracked = os.path.join(root, "paraiso_b200", "_generated", "LifeExampled_OO")

@@ -1,5 +1,5 @@
 """profiles/traffic.json from `ncu --set full` captures: DRAM bytes per launch of the dominant kernels, stamped with the hash of the
-generated kernel source they were taken from (bench.py reports `roofline.traffic` only while that source is the one loaded).
+generated kernel source (and the runtime header it includes) they were taken from (bench.py reports `roofline.traffic` only while that source is the one loaded).
 usage: stamp_traffic.py <life.ncu-rep> <hydro_fast.ncu-rep> <hydro_exact.ncu-rep>"""
 import csv
 import hashlib
@@ -29,10 +29,10 @@ def dram_bytes(rep):
 
 if __name__ == "__main__":
     table = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of one launch at the bench size, from the ncu --set full captures "
-                         "summarised in this directory; kernel_source_sha1_16 = sha1 of the generated <Name>_kernels.cu the capture ran"}
+                         "summarised in this directory; kernel_source_sha1_16 = sha1 of the generated <Name>_kernels.cu + om_runtime.cuh the capture ran"}
     for (key, src, alg), rep in zip(ENTRIES, sys.argv[1:4]):
-        with open(os.path.join(GEN, src), "rb") as f:
-            h = hashlib.sha1(f.read()).hexdigest()[:16]
+        with open(os.path.join(GEN, src), "rb") as f, open(os.path.join(GEN, os.path.dirname(src), "om_runtime.cuh"), "rb") as r:
+            h = hashlib.sha1(f.read() + r.read()).hexdigest()[:16]
         b = dram_bytes(rep)
         table[key] = {"dram_bytes_per_launch": b, "algorithmic_bytes": alg, "ratio": round(b / alg, 4), "kernel_source_sha1_16": h,
                       "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_ncu.txt")}
