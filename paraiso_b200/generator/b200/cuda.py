@@ -176,6 +176,13 @@ class StageEmitter:
         if self.grouped:
             for i in self.ring_inputs:
                 self.depth[i.vid] = 2 * self.U
+        # warp-private rings (Tuning.warp_rings): every warp stages its own 32 V columns plus its own copy of the pads, so a row
+        # that enters the window only has to be ordered among the lanes of one warp — __syncwarp instead of a CTA barrier per row
+        self.warp_rings = (self.window and not self.bulk and not self.grouped and bool(getattr(self.tuning, "warp_rings", False))
+                           and NT % 32 == 0 and NT > 32)
+        if self.warp_rings:
+            self.RWW = self.PL + 32 * V + self.PR      # one warp's segment of a ring row
+            self.RW = (NT // 32) * self.RWW
         # inputs read without staging (column offset 0 only) are prefetched one row ahead into registers
         self.direct_pf = bool(self.tuning.direct_prefetch) and not self.window
         # rows touched outside [own_r0, own_r1): must stay inside the apron the ABI requires
@@ -586,10 +593,16 @@ class StageEmitter:
                 if ln not in self.pre:
                     self.pre.append(ln)
                 B.append(f"om_cp_async<{nb}>(&ring{v}[{so} + tb], src{v}, {nb});")
-                if self.PL:
-                    B.append(f"if (tid < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + tid * V], src{v} - PL, {nb});")
-                if self.PR:
-                    B.append(f"if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
+                if self.warp_rings:      # the pads of this warp's own segment
+                    if self.PL:
+                        B.append(f"if (lane < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + wb + lane * V], src{v} - PL, {nb});")
+                    if self.PR:
+                        B.append(f"if (lane < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + wb + PL + 32 * V + lane * V], src{v} + 32 * V, {nb});")
+                else:
+                    if self.PL:
+                        B.append(f"if (tid < {self.PL // V}) om_cp_async<{nb}>(&ring{v}[{so} + tid * V], src{v} - PL, {nb});")
+                    if self.PR:
+                        B.append(f"if (tid < {self.PR // V}) om_cp_async<{nb}>(&ring{v}[{so} + PL + NT * V + tid * V], src{v} + NT * V, {nb});")
                 B.append(f"src{v} += g.pitch;")
             B.append("}")
             B.append("om_cp_async_commit();")
@@ -643,7 +656,7 @@ class StageEmitter:
                 B: List[str] = []
                 if not self.grouped:
                     stage_inputs(B, 0)
-                    B.append("__syncthreads();")
+                    B.append("__syncwarp();   // the row's segment was staged by this warp's own lanes" if self.warp_rings else "__syncthreads();")
                 B.append("// the row that enters the stencil window: shared memory -> registers, once")
                 for i in self.ring_inputs:
                     b, T = i.vid, self.T(i.vid)
@@ -723,7 +736,12 @@ class StageEmitter:
         E(f"__global__ void {lb} {self.name}_kernel({', '.join(params)}) {{")
         E(f"  constexpr int V = {V}, NT = {NT}, HL = {self.HL}, PL = {self.PL}, RW = {self.RW}, W_OUT = {self.W_OUT};")
         E("  const int tid = threadIdx.x;")
-        E("  const int tb = PL + tid * V;                           // this thread's element offset inside a ring row")
+        if self.warp_rings:
+            E(f"  constexpr int RWW = {self.RWW};                          // one warp's segment of a ring row: its 32 V columns between its own pads")
+            E("  const int lane = tid & 31, wb = (tid >> 5) * RWW;")
+            E("  const int tb = wb + PL + lane * V;                     // this thread's element offset inside a ring row")
+        else:
+            E("  const int tb = PL + tid * V;                           // this thread's element offset inside a ring row")
         E("  OM_DYNAMIC_SMEM(om_smem);")
         off = 0
         for v, d in self.depth.items():

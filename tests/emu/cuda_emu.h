@@ -71,6 +71,7 @@ struct EmuBlock {
 static EmuBlock* emu_block;
 
 static inline void __syncthreads() { emu_block->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_block->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
 static inline int __syncthreads_or(int pred) {
   if (pred) __atomic_fetch_or(&emu_block->vote, 1u, __ATOMIC_SEQ_CST);
   emu_block->bar->arrive_and_wait();

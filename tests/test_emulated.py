@@ -15,14 +15,15 @@ from paraiso_b200.runtime import Machine
 from tests.emu.build_emu import build_emulated
 
 
-def _life(size, steps, mode, window=True, staging="cp_async", cold=False, clean=False):
+def _life(size, steps, mode, window=True, staging="cp_async", cold=False, clean=False, warp=False):
     setup = life_setup("master", size=size)
     setup.tuning.skeleton = mode
     setup.tuning.row_window = window
     setup.tuning.staging = staging
     setup.tuning.cold_rare = cold
     setup.tuning.clean_ctas = clean
-    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}" + ("_cold" if cold else "") + ("_clean" if clean else ""))
+    setup.tuning.warp_rings = warp
+    desc, so = build_emulated(setup, life_om("master"), tag=f"Life_{mode}_{int(window)}_{staging}" + ("_cold" if cold else "") + ("_clean" if clean else "") + ("_warp" if warp else ""))
     with open(os.path.join(os.path.dirname(so), "Life_kernels.cu")) as f:
         src = f.read()
     assert ("register streaming" in src) == (mode == "stream")
@@ -30,6 +31,7 @@ def _life(size, steps, mode, window=True, staging="cp_async", cold=False, clean=
     assert ("om_bulk_g2s" in src) == (staging == "bulk")
     assert ("const OmRare om_rr = [=]() __attribute__((noinline))" in src) == cold
     assert ("const bool cta_rare = __syncthreads_or(rare);" in src) == clean
+    assert ("__syncwarp();   // the row's segment was staged by this warp's own lanes" in src) == warp
     m = Machine(desc, so, size=size, device="cpu", _emulated=True)
     o = OracleMachine(life_setup("master", size=size), life_om("master"))
     init = (np.random.default_rng(7).random((size[1], size[0])) < 0.35).astype(np.int32)
@@ -60,6 +62,13 @@ def test_life_with_row_bodies_for_ctas_without_a_rare_block(size):
     """Tuning.clean_ctas: CTAs that are neither an edge strip nor a chunk with a y wrap (the 1600-wide grid has them) run copies of
     the row bodies without the rarely taken block."""
     _life(size, 4, "ring", clean=True)
+
+
+@pytest.mark.parametrize("size", [(80, 48), (5, 3), (513, 40), (1030, 37), (1, 1), (2, 2), (1, 7), (7, 1), (80, 100), (600, 130), (1600, 70)])
+def test_life_with_warp_private_rings(size):
+    """Tuning.warp_rings: every warp stages its own segment of a ring row (its own copy of the pads included) and the row loop
+    has no CTA barrier."""
+    _life(size, 4, "ring", warp=True)
 
 
 @pytest.mark.parametrize("size", [(80, 48), (513, 40)])

@@ -19,7 +19,12 @@ CASES = {
     # (..., store hint, staging)
     "d": [(6, 16, 9, False, "", "cp_async"), (6, 16, 9, False, "cs", "cp_async"), (6, 16, 9, False, "cg", "cp_async"), (6, 16, 9, False, "", "bulk"),
           (3, 16, 9, False, "", "bulk"), (6, 16, 9, False, "cs", "bulk")],
-}[next((a for a in sys.argv[1:] if a in ("a", "b", "c", "d")), "a")]
+    # (..., Tuning.warp_rings)
+    "e": [(6, 16, 9, False, "", "cp_async", False), (6, 16, 9, False, "", "cp_async", True), (4, 16, 9, False, "", "cp_async", True),
+          (8, 16, 9, False, "", "cp_async", True), (6, 20, 9, False, "", "cp_async", True), (6, 12, 9, False, "", "cp_async", True),
+          (6, 24, 9, False, "", "cp_async", True), (6, 32, 9, False, "", "cp_async", True), (3, 20, 9, False, "", "cp_async", True),
+          (6, 16, 8, False, "", "cp_async", True), (6, 16, 10, False, "", "cp_async", True)],
+}[next((a for a in sys.argv[1:] if a in ("a", "b", "c", "d", "e")), "a")]
 size = (16384, 16384)
 if __name__ == "__main__":
     built = []
@@ -27,11 +32,12 @@ if __name__ == "__main__":
         pf, cr, minb = case[:3]
         clean = case[3] if len(case) > 3 else False
         hint, staging = (case[4], case[5]) if len(case) > 5 else ("", "cp_async")
+        warp = case[6] if len(case) > 6 else False
         s = life_setup("master")
         s.tuning.prefetch_rows, s.tuning.chunk_rows_light, s.tuning.min_blocks, s.tuning.clean_ctas = pf, cr, minb, clean
-        s.tuning.store_hint, s.tuning.staging = hint, staging
+        s.tuning.store_hint, s.tuning.staging, s.tuning.warp_rings = hint, staging, warp
         try:
-            built.append(((pf, cr, minb, clean, hint, staging), build_machine(s, life_om("master"), tag=f"variant_Life_pf{pf}_c{cr}_b{minb}_k{int(clean)}_{hint}_{staging}", verbose=True)))
+            built.append(((pf, cr, minb, clean, hint, staging, warp), build_machine(s, life_om("master"), tag=f"variant_Life_pf{pf}_c{cr}_b{minb}_k{int(clean)}_{hint}_{staging}_w{int(warp)}", verbose=True)))
         except Exception as e:
             print(json.dumps(dict(prefetch_rows=pf, chunk_rows=cr, min_blocks=minb, error=repr(e)[:200])), flush=True)
     if "--prebuild" in sys.argv:
@@ -41,16 +47,22 @@ if __name__ == "__main__":
     from paraiso_b200.runtime import Machine
     from paraiso_b200.tuning import measure
     seed = torch.from_numpy(life_seed(size[0], 0, size[1])).pin_memory()
+    ref = None
     for rep in range(2):
-        for (pf, cr, minb, clean, hint, staging), (desc, so) in built:
+        for (pf, cr, minb, clean, hint, staging, warp), (desc, so) in built:
             try:
                 m = Machine(desc, so, size=size)
                 m.call("init")
                 m.set_from_host("cell", seed)
                 st = m.kernels["proceed"]["stages"][0]
                 ms = min(measure(m, "proceed", steps=20, stage=0) for _ in range(3))
-                print(json.dumps(dict(prefetch_rows=pf, chunk_rows=cr, min_blocks=minb, clean_ctas=clean, store_hint=hint, staging=staging, occupancy=getattr(m.lib, st["symbol"] + "_occupancy")(),
-                                      chunks=m._geom(st).nchunks, ms=ms, GBs=2 * 4 * size[0] * size[1] / ms / 1e6)), flush=True)
+                m.set_from_host("cell", seed)
+                for _ in range(3):
+                    m.call("proceed")
+                got = (int(m.get("cell").astype("int64").sum()), int(m.scalar("population")))
+                ref = ref or got
+                print(json.dumps(dict(prefetch_rows=pf, chunk_rows=cr, min_blocks=minb, clean_ctas=clean, store_hint=hint, staging=staging, warp_rings=warp, occupancy=getattr(m.lib, st["symbol"] + "_occupancy")(),
+                                      chunks=m._geom(st).nchunks, ms=ms, GBs=2 * 4 * size[0] * size[1] / ms / 1e6, same_result=(got == ref))), flush=True)
                 del m
             except Exception as e:
                 print(json.dumps(dict(prefetch_rows=pf, chunk_rows=cr, min_blocks=minb, error=repr(e)[:200])), flush=True)
