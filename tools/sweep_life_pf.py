@@ -24,7 +24,8 @@ CASES = {
           (8, 16, 9, False, "", "cp_async", True), (6, 20, 9, False, "", "cp_async", True), (6, 12, 9, False, "", "cp_async", True),
           (6, 24, 9, False, "", "cp_async", True), (6, 32, 9, False, "", "cp_async", True), (3, 20, 9, False, "", "cp_async", True),
           (6, 16, 8, False, "", "cp_async", True), (6, 16, 10, False, "", "cp_async", True)],
-}[next((a for a in sys.argv[1:] if a in ("a", "b", "c", "d", "e")), "a")]
+    "f": [(6, 16, 9), (6, 15, 9), (6, 17, 9), (7, 15, 9), (7, 17, 9), (5, 17, 9), (5, 15, 9), (7, 18, 9), (8, 17, 9)],
+}[next((a for a in sys.argv[1:] if a in ("a", "b", "c", "d", "e", "f")), "a")]
 size = (16384, 16384)
 if __name__ == "__main__":
     built = []
