@@ -239,8 +239,9 @@ class Machine:
             # light streaming stages: short chunks (Tuning.chunk_rows_light, measured in profiles/r1_life_sweep.txt)
             # keep the set of concurrently streamed rows compact; warm-up rows are L2 hits.  The count is then rounded to
             # whole waves of resident CTAs (sms * occ) when that moves it by less than 8 % (Life 16384^2: 1024 -> 1040 chunks =
-            # 25.0 waves).  Measured, the kernel is NOT wave-quantised — flat within 1.5 % from 13 to 24 waves
-            # (profiles/r2o_life_chunks.jsonl) — so this only keeps the grid regular; the height itself is what matters
+            # 25.0 waves).  Measured, the kernel is hardly wave-quantised — flat within 1.5 % from 13 to 24 waves
+            # (profiles/r2o_life_chunks.jsonl); on the final kernel 1040 chunks run 0.6 % faster than the unrounded 1024 and
+            # 0.4-1.2 % faster than 915 ... 1165 (profiles/r2ar_life_chunkcount.jsonl): the height itself is what matters most
             chunks = max(1, nrows // st["chunk_rows"])
             wave = sms * occ
             k = max(1, round(strips * chunks * layers / wave))
